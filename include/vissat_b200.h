@@ -1,0 +1,175 @@
+/*
+ * vissat_b200.h — C ABI of libvissat_b200.so: the sm_100a implementation of VisSat's aggregate_2p5d hot path.
+ *
+ * The reference (Kai-46/VisSatSatelliteStereo) is pure Python and has no FFI layer; its boundary for this
+ * path is the Python function surface of SURVEY.md §8(b).  This header is what a ctypes binding of that
+ * surface calls.  Each entry point names the reference lines it replaces (paths relative to the reference
+ * repository root).
+ *
+ * Conventions
+ *   - plain C types only; every pointer marked "dev" is device memory owned by the caller
+ *     (e.g. torch.Tensor.data_ptr()); "host" pointers are host memory.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  Kernels are enqueued on it and
+ *     the call returns without synchronising unless stated.
+ *   - return value: 0 = ok, non-zero = error; vs_last_error() returns a thread-local message.
+ *     No C++ exception crosses the ABI.  There is no CPU fallback: without a CUDA device every compute
+ *     entry point fails with VS_ERR_CUDA.
+ *   - a vs_ctx belongs to one device and must not be used from two host threads at once.
+ */
+#ifndef VISSAT_B200_H
+#define VISSAT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VS_OK 0
+#define VS_ERR_INVALID 1 /* bad argument */
+#define VS_ERR_CUDA 2    /* CUDA runtime error (message has the cudaError string) */
+#define VS_ERR_STATE 3   /* call order (e.g. rasterize before vs_set_aoi) */
+#define VS_ERR_FIT 4     /* AOI polynomial could not be validated; exact mode is still available */
+
+#define VS_ABI_VERSION 1
+
+typedef struct vs_ctx vs_ctx;
+
+/* AOI + grid description.
+ * Built from aoi.json exactly as the reference does:
+ *   lat0/lon0/alt0  coordinate_system.py:45-47   (bbox centre, alt_min)
+ *   zone/south      lib/latlon_utm_converter.py:43-50 (the reference derives them from the first valid point
+ *                   of every view; for an AOI inside one zone they equal aoi.json's zone_number/hemisphere)
+ *   ul_e/ul_n       produce_dsm.py:51-52
+ *   xsize/ysize     produce_dsm.py:54-55 (e_size, n_size)
+ *   row_res/col_res lib/proj_to_grid.py:42-43: row = floor((ul_n - N)/row_res), col = floor((E - ul_e)/col_res).
+ *                   NOTE the reference divides rows by its `xresolution` and columns by `yresolution`;
+ *                   the caller passes them here already in that (swapped-name) order.
+ *   alt_lo/alt_hi   altitude range (metres, absolute) over which the fast ENU->grid polynomial is fitted and
+ *                   validated; points outside it take the exact per-point chain.  aoi.json alt_min/alt_max
+ *                   widened by the caller is a good choice.
+ */
+typedef struct vs_aoi {
+    double lat0, lon0, alt0;
+    int32_t zone;
+    int32_t south; /* 1 = southern hemisphere */
+    double ul_e, ul_n;
+    double row_res, col_res;
+    int32_t xsize, ysize;
+    double alt_lo, alt_hi;
+} vs_aoi;
+
+/* Diagnostics of the per-AOI polynomial that replaces pymap3d.enu2geodetic + PROJ utm inside the fused
+ * rasteriser (validated against the exact device chain at vs_set_aoi time). */
+typedef struct vs_fit_info {
+    int32_t degree;          /* 3..5, or 0 = exact chain for every point */
+    int32_t n_terms;
+    double max_err_cells;    /* max |poly - exact| of the fractional row/col on held-out points */
+    double max_err_alt_m;    /* max |poly - exact| altitude (m) on held-out points */
+    double box_center[3];    /* ENU box the polynomial covers */
+    double box_half[3];
+} vs_fit_info;
+
+/* Per-call counters written by the rasterisers (device memory, 4 x uint64, zeroed by the call). */
+#define VS_STAT_VALID 0     /* pixels/points with a finite position              (aggregate_2p5d_util.py:92) */
+#define VS_STAT_INGRID 1    /* of those, inside the grid                          (lib/proj_to_grid.py:48)    */
+#define VS_STAT_AMBIGUOUS 2 /* in-grid points whose fractional row/col is within `ambiguity_eps` cells of a cell
+                               edge: their floor() may legitimately differ from the float64 CPU chain         */
+#define VS_STAT_EXACT 3     /* points that took the exact per-point chain (outside the fitted altitude range) */
+#define VS_NUM_STATS 4
+
+/* ---- context ------------------------------------------------------------------------------------------ */
+int vs_abi_version(void);
+const char* vs_last_error(void);
+int vs_device_count(int* out);
+int vs_ctx_create(int device, vs_ctx** out);
+int vs_ctx_destroy(vs_ctx* ctx);
+
+/* Fit + validate the ENU->(row, col, alt) polynomial for this AOI (synchronous, ~ms).
+ * max_degree: 3..5; 0 forces the exact chain for every point.  info may be NULL. */
+int vs_set_aoi(vs_ctx* ctx, const vs_aoi* aoi, int max_degree, vs_fit_info* info);
+int vs_set_ambiguity_eps(vs_ctx* ctx, double eps_cells); /* default 1e-7 */
+
+/* ---- stage A: depth map -> max-height key grid ---------------------------------------------------------
+ * Replaces aggregate_2p5d_util.py:75-98 (NaN-ing, pixel grid, M*[col,row,1,depth], perspective divide,
+ * local_to_global, latlon_to_eastnorh) fused with lib/proj_to_grid.py:42-61 (cell index, bounds mask,
+ * per-cell nanmax).  `keygrid` holds ysize*xsize uint32 keys: 0 = empty, otherwise the order-preserving
+ * image of the float32-rounded altitude (rounding is monotone, so max commutes with it).
+ *   depth        dev float32 H*W, row-major (colmap/read_dense.py:36-51 layout); values <= 0 are invalid
+ *   inv_proj_mat host 16 doubles, row-major 4x4 (one inv_proj_mats.txt row, aggregate_2p5d_util.py:54-61)
+ *   keygrid      dev uint32 ysize*xsize; cleared by the call when clear_first != 0
+ *   height_map   dev float32 H*W or NULL: ENU-up per pixel, NaN where invalid (aggregate_2p5d_util.py:91)
+ *   stats        dev uint64[VS_NUM_STATS] or NULL
+ */
+int vs_unproject_rasterize(vs_ctx* ctx, const float* depth, int32_t H, int32_t W, const double* inv_proj_mat,
+                           uint32_t* keygrid, int clear_first, float* height_map, uint64_t* stats, void* stream);
+
+/* lib/proj_to_grid.py:42-61 for explicit points: dev float64 N*3 rows (E, N, alt) in the grid's UTM frame.
+ * Exact float64 semantics: keygrid64 holds uint64 keys of the float64 altitude (0 = empty).
+ * Grid geometry is passed explicitly (this is the public proj_to_grid signature, independent of vs_set_aoi). */
+int vs_points_rasterize(vs_ctx* ctx, const double* points, int64_t n_points, double xoff, double yoff,
+                        double xresolution, double yresolution, int32_t xsize, int32_t ysize,
+                        uint64_t* keygrid64, int clear_first, uint64_t* stats, void* stream);
+
+/* ---- stage B: key grid -> per-view DSM -------------------------------------------------------------------
+ * Replaces the 3x3 NaN-hole fill of lib/proj_to_grid.py:65-79 (median of the non-NaN neighbours read from the
+ * pre-fill grid, even count -> mean of the two middles) and produce_dsm.py:58 (astype(float32) +
+ * cv2.medianBlur(.,3), including OpenCV's NaN behaviour: SIMD min/max semantics on columns 1..W-2 when
+ * W >= simd_lanes+2, scalar semantics on the border columns; 1-D 3-tap median for single-row/column grids).
+ *   dsm_out   dev float32 ysize*xsize  (what the reference writes to dsm_tif/<view>.tif, NaN = empty)
+ *   nan_count dev uint64 or NULL: number of NaN cells in dsm_out (aggregate_2p5d.py:63 "empty ratio")
+ */
+int vs_grid_finalize(vs_ctx* ctx, const uint32_t* keygrid, int32_t xsize, int32_t ysize, float* dsm_out,
+                     int simd_lanes, uint64_t* nan_count, void* stream);
+
+/* float64 variant for the public proj_to_grid API: decode + hole fill, no blur; filled64 is float64 ysize*xsize.
+ * If blurred32 != NULL also writes cv2.medianBlur(filled64.astype(float32), 3) (produce_dsm.py:58). */
+int vs_grid_finalize64(vs_ctx* ctx, const uint64_t* keygrid64, int32_t xsize, int32_t ysize, double* filled64,
+                       float* blurred32, int simd_lanes, void* stream);
+
+/* ---- stage C: cross-view fusion --------------------------------------------------------------------------
+ * Replaces aggregate_2p5d.py:65-78: per cell over V views (in the given order = sorted file order):
+ * count filter (<= 2 measurements -> NaN), np.nanmedian, MAD = nanmedian(|x - med|), reject |x - med| > MAD,
+ * np.nanmean of the survivors with numpy's float32 pairwise summation order.
+ *   views        dev float32: plane v starts at views + v*plane_stride (elements); each plane is rows*W row-major
+ *   out_mean     dev float32 rows*W
+ * (The NaN<->nodata round trip of lib/dsm_util.py:69-72,128-131 is an identity for heights further than 0.1 m
+ *  from -10000 and is applied by the host-side tif reader when fusing from files.)
+ */
+int vs_fuse_views(vs_ctx* ctx, const float* views, int64_t plane_stride, int32_t n_views, int32_t rows, int32_t W,
+                  float* out_mean, void* stream);
+
+/* aggregate_2p5d.py:81 (and the blur half of produce_dsm.py:58): cv2.medianBlur(float32, 3) on rows
+ * [row_begin, row_end) of an image of H_total rows.  `in` points at image row `in_row0`; rows
+ * max(row_begin-1,0)..min(row_end,H_total-1) must be present in it (row-band halo for multi-GPU fusion).
+ * `out` points at output row row_begin.  nan_count as above (counts only the rows written). */
+int vs_median3x3(vs_ctx* ctx, const float* in, int32_t in_row0, int32_t H_total, int32_t W, int32_t row_begin,
+                 int32_t row_end, float* out, int simd_lanes, uint64_t* nan_count, void* stream);
+
+/* ---- exact converters (public converter API, float64 chain, one thread per point) ------------------------
+ * lib/latlonalt_enu_converter.py:42-45  (pymap3d.enu2geodetic)   */
+int vs_enu_to_geodetic(vs_ctx* ctx, const double* e, const double* n, const double* u, int64_t count, double lat0,
+                       double lon0, double alt0, double* lat, double* lon, double* alt, void* stream);
+/* lib/latlonalt_enu_converter.py:36-39  (pymap3d.geodetic2enu)   */
+int vs_geodetic_to_enu(vs_ctx* ctx, const double* lat, const double* lon, const double* alt, int64_t count,
+                       double lat0, double lon0, double alt0, double* e, double* n, double* u, void* stream);
+/* lib/latlon_utm_converter.py:50-51     (pyproj utm forward, PROJ etmerc order 6) */
+int vs_geodetic_to_utm(vs_ctx* ctx, const double* lat, const double* lon, int64_t count, int32_t zone, int32_t south,
+                       double* east, double* north, void* stream);
+/* lib/latlon_utm_converter.py:61-62     (pyproj utm inverse)     */
+int vs_utm_to_geodetic(vs_ctx* ctx, const double* east, const double* north, int64_t count, int32_t zone,
+                       int32_t south, double* lat, double* lon, void* stream);
+/* aggregate_2p5d_util.py:96-98 in one pass: ENU -> (E, N, alt) through the exact chain. */
+int vs_enu_to_utm(vs_ctx* ctx, const double* e, const double* n, const double* u, int64_t count, double lat0,
+                  double lon0, double alt0, int32_t zone, int32_t south, double* east, double* north, double* alt,
+                  void* stream);
+
+/* ---- introspection ---------------------------------------------------------------------------------------
+ * Number of kernel launches issued by this library since the context was created (for bench.py's
+ * gpu_launches claim). */
+int vs_launch_count(vs_ctx* ctx, uint64_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VISSAT_B200_H */

@@ -1,0 +1,288 @@
+"""GPU parity: the CUDA path (through the C ABI) against the oracle and the reference-run golden vectors.
+
+Bars (BASELINE.json north_star): cell indices, occupancy masks and median selection bit-exact; heights within
+1e-3 m.  Where float64 rounding noise of the CPU chain itself (~1e-9 m) can legitimately move a point across a
+cell edge or flip the strict `abs(x-med) > mad` test, the tests audit it instead of hiding it.
+"""
+import json
+
+import cv2
+import numpy as np
+import pytest
+import torch
+
+from oracle import geodesy, pipeline as op
+
+pytestmark = pytest.mark.gpu
+
+HEIGHT_TOL = 1e-3   # metres, north_star
+
+
+def _eq(a, b):
+    return np.array_equal(a, b, equal_nan=True)
+
+
+@pytest.fixture(scope='module')
+def lanes():
+    return op.detect_cv2_simd_lanes()
+
+
+@pytest.fixture(scope='module')
+def eng_mod():
+    from vissatsatellitestereo_b200 import engine
+    engine.require_cuda()
+    return engine
+
+
+# ------------------------------------------------------------------------------------------------ converters
+def test_exact_converters_vs_oracle(eng_mod):
+    from vissatsatellitestereo_b200.lib import latlonalt_enu_converter as C1, latlon_utm_converter as C2
+    rng = np.random.default_rng(1)
+    n = 20000
+    lat0, lon0, alt0 = -34.4899, -58.5856, -30.0
+    e = rng.uniform(-3000, 3000, (n, 1))
+    nn = rng.uniform(-3000, 3000, (n, 1))
+    u = rng.uniform(-100, 400, (n, 1))
+    lat, lon, alt = C1.enu_to_latlonalt(e, nn, u, lat0, lon0, alt0)
+    olat, olon, oalt = geodesy.enu_to_latlonalt(e, nn, u, lat0, lon0, alt0)
+    assert lat.shape == (n, 1)
+    # 1e-8 m == 9e-14 deg; float64 chain noise is ~1e-9 m
+    assert np.abs(lat - olat).max() * 111e3 < 2e-8 and np.abs(lon - olon).max() * 111e3 < 2e-8
+    assert np.abs(alt - oalt).max() < 2e-8
+    east, north = C2.latlon_to_eastnorh(lat, lon)
+    oe, on = geodesy.latlon_to_eastnorh(olat, olon)
+    assert np.abs(east - oe).max() < 3e-8 and np.abs(north - on).max() < 3e-8
+    la2, lo2 = C2.eastnorth_to_latlon(east, north, 21, 'S')
+    ola2, olo2 = geodesy.eastnorth_to_latlon(oe, on, 21, 'S')
+    assert np.abs(la2 - ola2).max() * 111e3 < 3e-8 and np.abs(lo2 - olo2).max() * 111e3 < 3e-8
+    e2, n2, u2 = C1.latlonalt_to_enu(lat, lon, alt, lat0, lon0, alt0)
+    assert np.abs(e2 - e).max() < 3e-8 and np.abs(n2 - nn).max() < 3e-8 and np.abs(u2 - u).max() < 3e-8
+    # scalars in -> scalars out (lib/latlonalt_enu_converter.py:49-58 sample)
+    es, ns, us = C1.latlonalt_to_enu(-34.450, -58.579, 20.31, -34.448, -58.577, -30.0)
+    assert isinstance(es, float)
+    assert abs(es + 183.79014029) < 1e-6 and abs(ns + 221.86356704) < 1e-6 and abs(us - 50.30348255) < 1e-6
+    # published known answers
+    E, N = C2.latlon_to_eastnorh(np.array([[56.0]]), np.array([[12.0]]))
+    assert abs(E[0, 0] - 687071.44) < 0.006 and abs(N[0, 0] - 6210141.33) < 0.006
+    # northern hemisphere + both of the reference's __main__ samples
+    for s in (1, -1):
+        la = np.array([[s * 47.9941214]])
+        lo = np.array([[7.8509671]])
+        E, N = C2.latlon_to_eastnorh(la, lo)
+        oE, oN = geodesy.latlon_to_eastnorh(la, lo)
+        assert abs(E[0, 0] - oE[0, 0]) < 1e-8 and abs(N[0, 0] - oN[0, 0]) < 1e-8
+
+
+# ------------------------------------------------------------------------------------------------ proj_to_grid
+@pytest.mark.parametrize('k', range(5))
+def test_proj_to_grid_bit_exact_vs_reference_golden(golden, eng_mod, k):
+    from vissatsatellitestereo_b200.lib.proj_to_grid import proj_to_grid
+    pts = golden['ptg{}_points'.format(k)]
+    xoff, yoff, xres, yres, xs, ys = golden['ptg{}_args'.format(k)]
+    got = proj_to_grid(pts, xoff, yoff, xres, yres, int(xs), int(ys))
+    assert got.dtype == np.float64
+    assert _eq(got, golden['ptg{}_dsm'.format(k)])
+
+
+def test_proj_to_grid_large_random_vs_oracle(eng_mod):
+    from vissatsatellitestereo_b200.lib.proj_to_grid import proj_to_grid
+    rng = np.random.default_rng(3)
+    n, xs, ys = 400000, 301, 257
+    pts = np.stack([1000 + rng.uniform(-5, xs * 0.3 + 5, n), 5000 - rng.uniform(-5, ys * 0.3 + 5, n),
+                    rng.normal(20, 30, n)], 1)
+    pts = pts[(pts[:, 0] < 1030) | (pts[:, 0] > 1045)]     # a NaN band wider than the 3x3 fill
+    pts[rng.random(pts.shape[0]) < 0.01, 2] = np.nan
+    got = proj_to_grid(pts, 1000.0, 5000.0, 0.3, 0.3, xs, ys)
+    want = op.proj_to_grid_fast(pts, 1000.0, 5000.0, 0.3, 0.3, xs, ys)
+    assert _eq(got, want)
+    # empty input -> all-NaN grid
+    assert np.isnan(proj_to_grid(np.zeros((0, 3)), 0.0, 0.0, 1.0, 1.0, 4, 3)).all()
+
+
+# ------------------------------------------------------------------------------------------------ medianBlur
+@pytest.mark.parametrize('shape', [(1, 1), (1, 9), (9, 1), (2, 2), (3, 3), (5, 17), (6, 18), (40, 33), (33, 70), (257, 131)])
+def test_median3x3_bit_exact_vs_cv2(eng_mod, lanes, shape):
+    from vissatsatellitestereo_b200 import synthetic as S
+    eng = _tiny_engine(eng_mod, lanes)
+    rng = np.random.default_rng(shape[0] * 1000 + shape[1])
+    for nan_frac in (0.0, 0.3, 0.8):
+        img = rng.normal(size=shape).astype(np.float32)
+        img[rng.random(shape) < nan_frac] = np.nan
+        got = eng.median3x3(torch.from_numpy(img).cuda()).cpu().numpy()
+        assert _eq(got, cv2.medianBlur(img, 3)), (shape, nan_frac)
+    # row-band form (multi-GPU fusion): rows [r0, r1) from a buffer holding rows r0-1 .. r1
+    if shape[0] >= 8 and shape[1] > 1:
+        img = rng.normal(size=shape).astype(np.float32)
+        img[rng.random(shape) < 0.3] = np.nan
+        want = cv2.medianBlur(img, 3)
+        r0, r1 = 3, shape[0] - 2
+        band = torch.from_numpy(np.ascontiguousarray(img[r0 - 1:r1 + 1])).cuda()
+        got = eng.median3x3(band, row_begin=r0, row_end=r1, in_row0=r0 - 1, h_total=shape[0]).cpu().numpy()
+        assert _eq(got, want[r0:r1])
+
+
+_TINY = {}
+
+
+def _tiny_engine(eng_mod, lanes):
+    if 'e' not in _TINY:
+        from vissatsatellitestereo_b200 import synthetic as S
+        cfg = S.scaled(S.CONFIGS['C1'], views=1, depth=64, grid=32)
+        _TINY['e'] = eng_mod.DsmEngine(S.make_aoi(cfg, geodesy), cfg.res, cfg.res, simd_lanes=lanes)
+    return _TINY['e']
+
+
+# ------------------------------------------------------------------------------------------------ fusion alone
+@pytest.mark.parametrize('V', [1, 2, 3, 4, 7, 8, 9, 16, 23, 33, 50, 56, 57, 64, 65, 100, 129, 200, 300])
+def test_fusion_bit_exact_vs_numpy(eng_mod, lanes, V):
+    eng = _tiny_engine(eng_mod, lanes)
+    rng = np.random.default_rng(V)
+    H, W = 37, 53
+    cube = (30 + 5 * rng.normal(size=(V, H, W))).astype(np.float32)
+    cube[rng.random(cube.shape) < 0.35] = np.nan
+    cube[:, 0, 0] = np.nan
+    cube[2:, 0, 1] = np.nan
+    cube[:, 0, 2] = 7.25
+    cube[:, 1, :] = np.round(cube[:, 1, :])          # many ties
+    cube[:, 2, :] = np.where(rng.random((V, W)) < 0.5, 3.0, 4.0).astype(np.float32)
+    want = op.fuse_dsms([cube[v].copy() for v in range(V)], blur=False)
+    got = eng.fuse(torch.from_numpy(cube).cuda()).cpu().numpy()
+    assert _eq(got, want)
+
+
+@pytest.mark.parametrize('case', ['c1', 'c5', 'c3'])
+def test_fusion_of_reference_per_view_dsms_bit_exact(golden, eng_mod, lanes, case):
+    """Stage C + final blur fed with the reference's own per-view DSMs == the reference's fused DSM."""
+    aoi = json.loads(str(golden[case + '_aoi']))
+    res = float(golden[case + '_res'])
+    eng = eng_mod.DsmEngine(aoi, res, res, simd_lanes=lanes)
+    pv = torch.from_numpy(golden[case + '_per_view']).cuda()
+    got = eng.fuse_and_blur(pv).cpu().numpy()
+    assert _eq(got, golden[case + '_fused'])
+    assert eng.last_nan_count() == int(np.isnan(golden[case + '_fused']).sum())
+
+
+# ------------------------------------------------------------------------------------------------ stage A + B
+def _ambiguous_cells(depth, M, aoi, res, eps_cells):
+    """Cells that a point within eps of a cell edge could move into / out of (oracle-side audit)."""
+    _, pts = op.unproject_depth(depth, M)
+    utm = op.enu_points_to_utm(pts, aoi)
+    e_size, n_size = op.grid_shape(aoi, res, res)
+    rowf = (aoi['ul_northing'] - utm[:, 1]) / res
+    colf = (utm[:, 0] - aoi['ul_easting']) / res
+    fr = rowf - np.floor(rowf)
+    fc = colf - np.floor(colf)
+    amb = (fr < eps_cells) | (fr > 1 - eps_cells) | (fc < eps_cells) | (fc > 1 - eps_cells)
+    mask = np.zeros((n_size, e_size), dtype=bool)
+    r = np.floor(rowf[amb]).astype(int)
+    c = np.floor(colf[amb]).astype(int)
+    for dr in (-1, 0, 1):
+        for dc in (-1, 0, 1):
+            rr, cc = r + dr, c + dc
+            ok = (rr >= 0) & (rr < n_size) & (cc >= 0) & (cc < e_size)
+            mask[rr[ok], cc[ok]] = True
+    return mask, int(amb.sum())
+
+
+@pytest.mark.parametrize('case', ['c1', 'c5', 'c3'])
+def test_per_view_dsm_vs_reference_golden(golden, eng_mod, lanes, case):
+    aoi = json.loads(str(golden[case + '_aoi']))
+    res = float(golden[case + '_res'])
+    eng = eng_mod.DsmEngine(aoi, res, res, simd_lanes=lanes)
+    assert eng.fit['degree'] >= 3, eng.fit
+    depths, mats, want = golden[case + '_depths'], golden[case + '_mats'], golden[case + '_per_view']
+    n_exact_bits = n_cells = 0
+    for v in range(depths.shape[0]):
+        got = eng.view_dsm(torch.from_numpy(depths[v]).cuda(), mats[v]).cpu().numpy()
+        st = eng.stats()
+        _, pts = op.unproject_depth(depths[v], mats[v])
+        assert st['valid'] == pts.shape[0]
+        assert st['exact'] == 0
+        allow = np.zeros(want[v].shape, dtype=bool)
+        if st['ambiguous']:
+            amb_mask, _ = _ambiguous_cells(depths[v], mats[v], aoi, res, 1e-7)
+            allow = cv2.dilate(amb_mask.astype(np.uint8), np.ones((5, 5), np.uint8)).astype(bool)
+        # occupancy mask bit-exact
+        assert np.array_equal(np.isnan(got)[~allow], np.isnan(want[v])[~allow]), 'view {}'.format(v)
+        diff = np.abs(got.astype(np.float64) - want[v].astype(np.float64))
+        diff[np.isnan(diff)] = 0
+        assert diff[~allow].max() <= HEIGHT_TOL, 'view {} max diff {}'.format(v, diff[~allow].max())
+        n_exact_bits += int(np.sum((got == want[v]) | (np.isnan(got) & np.isnan(want[v]))))
+        n_cells += got.size
+    # the polynomial reproduces the float64 chain to ~1e-9 m, so almost every float32 height is identical
+    assert n_exact_bits / n_cells > 0.995, n_exact_bits / n_cells
+
+
+@pytest.mark.parametrize('case', ['c1', 'c5', 'c3'])
+def test_end_to_end_vs_reference_golden(golden, eng_mod, lanes, case):
+    aoi = json.loads(str(golden[case + '_aoi']))
+    res = float(golden[case + '_res'])
+    eng = eng_mod.DsmEngine(aoi, res, res, simd_lanes=lanes)
+    depths, mats = golden[case + '_depths'], golden[case + '_mats']
+    V = depths.shape[0]
+    stack = torch.empty((V, eng.n_size, eng.e_size), dtype=torch.float32, device='cuda')
+    n_amb = 0
+    for v in range(V):
+        eng.view_dsm(torch.from_numpy(depths[v]).cuda(), mats[v], out=stack[v])
+        n_amb += eng.stats()['ambiguous']
+    got = eng.fuse_and_blur(stack).cpu().numpy()
+    want = golden[case + '_fused']
+    fragile = op.fusion_fragility([golden[case + '_per_view'][v] for v in range(V)])
+    fragile = cv2.dilate(fragile.astype(np.uint8), np.ones((3, 3), np.uint8)).astype(bool)
+    if n_amb == 0:
+        assert np.array_equal(np.isnan(got), np.isnan(want))
+    diff = np.abs(got.astype(np.float64) - want.astype(np.float64))
+    diff[np.isnan(diff)] = 0
+    bad = diff > HEIGHT_TOL
+    # a >1 mm difference is only acceptable where the reference's own strict MAD test sits on a float32 tie
+    assert not np.any(bad & ~fragile), 'unexplained cells: {}'.format(np.argwhere(bad & ~fragile)[:10])
+    assert bad.mean() < 0.01
+
+
+def test_exact_mode_and_altitude_fallback(golden, eng_mod, lanes):
+    """max_degree=0 runs the exact chain for every pixel; a narrow fitted altitude range sends points through
+    the per-point slow path.  Both must agree with the polynomial path."""
+    case = 'c1'
+    aoi = json.loads(str(golden[case + '_aoi']))
+    res = float(golden[case + '_res'])
+    depth = torch.from_numpy(golden[case + '_depths'][0]).cuda()
+    M = golden[case + '_mats'][0]
+    ref = eng_mod.DsmEngine(aoi, res, res, simd_lanes=lanes)
+    a = ref.view_dsm(depth, M).cpu().numpy()
+    exact = eng_mod.DsmEngine(aoi, res, res, simd_lanes=lanes, max_degree=0)
+    assert exact.fit['degree'] == 0
+    hm = torch.empty_like(depth)
+    b = exact.view_dsm(depth, M, height_map=hm).cpu().numpy()
+    assert exact.stats()['exact'] > 0
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    assert np.nanmax(np.abs(a - b)) <= 1e-4
+    height_map, _ = op.unproject_depth(golden[case + '_depths'][0], M)
+    assert np.array_equal(np.isnan(hm.cpu().numpy()), np.isnan(height_map))
+    assert np.nanmax(np.abs(hm.cpu().numpy() - height_map)) < 1e-4
+    hm2 = torch.empty_like(depth)
+    ref.view_dsm(depth, M, height_map=hm2)
+    assert _eq(hm2.cpu().numpy(), hm.cpu().numpy()) or np.nanmax(np.abs(hm2.cpu().numpy() - height_map)) < 1e-4
+    # narrow altitude range: alt_max below most of the terrain
+    aoi2 = dict(aoi)
+    aoi2['alt_max'] = aoi['alt_min'] + 1.0
+    import vissatsatellitestereo_b200.engine as E
+    narrow = eng_mod.DsmEngine(aoi, res, res, simd_lanes=lanes)
+    narrow._aoi = E.aoi_struct(aoi, res, res, alt_margin=(0.0, -100.0))   # alt_hi = alt_max - 100
+    narrow.fit = narrow.ctx.set_aoi(narrow._aoi, 5)
+    c = narrow.view_dsm(depth, M).cpu().numpy()
+    assert narrow.stats()['exact'] > 0
+    assert np.array_equal(np.isnan(a), np.isnan(c))
+    assert np.nanmax(np.abs(a - c)) <= 1e-4
+
+
+def test_errors_are_loud(eng_mod):
+    from vissatsatellitestereo_b200 import _native
+    ctx = _native.Context(0)
+    import ctypes as C
+    with pytest.raises(_native.VisSatError):
+        _native.check(_native.lib.vs_unproject_rasterize(ctx.handle, None, 4, 4, (C.c_double * 16)(), None, 1, None, None, None))
+    bad = _native.vs_aoi()
+    with pytest.raises(_native.VisSatError):
+        ctx.set_aoi(bad)
+    with pytest.raises(_native.VisSatError):
+        _native.Context(9999)

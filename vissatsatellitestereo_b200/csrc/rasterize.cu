@@ -1,0 +1,319 @@
+// Stage A kernels: depth map (or explicit points) -> per-cell max-height key grid.
+//
+// K1  k_unproject_scatter   aggregate_2p5d_util.py:75-98 + lib/proj_to_grid.py:42-61, fused.
+//     Streams the depth map with 16-byte loads (4 pixels per thread per step, grid-stride over a persistent
+//     grid sized to the SM count), unprojects in float64 (the matrix is pre-composed with the box
+//     normalisation so the perspective divide yields the polynomial's arguments directly), evaluates the
+//     per-AOI ENU->(col,row,alt) polynomial (aoi_fit.cu), and scatters with a no-return atomicMax (RED.MAX)
+//     on order-preserving float32 keys.  Consecutive pixels of one thread that fall in the same cell are
+//     merged in registers before the atomic.  Bound by the FP64 pipe and the L2 atomic units, not by HBM
+//     (4 bytes read per pixel); see DESIGN.md.
+// K1x k_unproject_scatter_exact  same scan, but only for pixels the polynomial does not cover (outside the
+//     fitted altitude range, or every pixel when the fit is disabled); exits at once when K1 counted none.
+// K1b k_points_scatter      lib/proj_to_grid.py:42-61 for explicit float64 (E,N,alt) rows, 64-bit keys.
+#include <math_constants.h>
+
+#include "geo_chain.cuh"
+#include "poly.cuh"
+#include "vs_common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+struct RasterParams {
+    double Mn[3][4];  // rows 0..2 of inv_proj_mat composed with the box normalisation: (M_i - c_i M_3) / h_i
+    double M3[4];     // row 3 (homogeneous w)
+    double half_z, center_z;  // to recover ENU-up from the normalised third coordinate
+    double eps;               // ambiguity threshold (cells)
+    int H, W;
+    int xsize, ysize;
+    int degree;
+};
+
+struct PolyCoefs {
+    double c[3][VS_MAX_TERMS];
+};
+
+__device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+template <int D>
+__device__ __forceinline__ void eval3(const PolyCoefs& pc, double u, double v, double w, double& colf, double& rowf,
+                                      double& alt) {
+    colf = vs_poly_eval<D>(pc.c[0], u, v, w);
+    rowf = vs_poly_eval<D>(pc.c[1], u, v, w);
+    alt = vs_poly_eval<D>(pc.c[2], u, v, w);
+}
+
+// block-level reduction of the per-thread counters, one atomic per counter per block
+__device__ __forceinline__ void flush_stats(unsigned long long* stats, unsigned v0, unsigned v1, unsigned v2, unsigned v3) {
+    if (stats == nullptr) return;
+    __shared__ unsigned s_acc[4];
+    if (threadIdx.x < 4) s_acc[threadIdx.x] = 0;
+    __syncthreads();
+    unsigned vals[4] = {v0, v1, v2, v3};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        unsigned r = __reduce_add_sync(0xffffffffu, vals[i]);
+        if ((threadIdx.x & 31) == 0 && r) atomicAdd(&s_acc[i], r);
+    }
+    __syncthreads();
+    if (threadIdx.x < 4 && s_acc[threadIdx.x]) atomicAdd(&stats[threadIdx.x], (unsigned long long)s_acc[threadIdx.x]);
+}
+
+template <int D>
+__global__ void __launch_bounds__(kThreads)
+k_unproject_scatter(RasterParams p, PolyCoefs pc, const float* __restrict__ depth, uint32_t* __restrict__ keygrid,
+                    float* __restrict__ height_map, unsigned long long* __restrict__ stats) {
+    const int64_t n_pix = (int64_t)p.H * p.W;
+    const int64_t n_chunks = (n_pix + 3) >> 2;
+    unsigned n_valid = 0, n_ingrid = 0, n_amb = 0, n_exact = 0;
+
+    for (int64_t chunk = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; chunk < n_chunks;
+         chunk += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t base = chunk << 2;
+        float d4[4];
+        if (base + 3 < n_pix) {
+            float4 t = ld_stream_f4(reinterpret_cast<const float4*>(depth + base));
+            d4[0] = t.x; d4[1] = t.y; d4[2] = t.z; d4[3] = t.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) d4[i] = (base + i < n_pix) ? depth[base + i] : -1.0f;
+        }
+        int row = (int)(base / p.W);
+        int col = (int)(base - (int64_t)row * p.W);
+        float hm[4];
+        int pend_cell = -1;      // register-level merge of same-cell neighbours
+        uint32_t pend_key = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            hm[i] = CUDART_NAN_F;
+            const float df = d4[i];
+            if (df > 0.0f && base + i < n_pix) {  // aggregate_2p5d_util.py:76 (NaN fails the test as well)
+                const double d = (double)df;
+                const double fc = (double)col, fr = (double)row;
+                // aggregate_2p5d_util.py:86-90: M . [col, row, 1, depth], then divide by w
+                const double hw = fma(p.M3[0], fc, fma(p.M3[1], fr, fma(p.M3[3], d, p.M3[2])));
+                const double rw = 1.0 / hw;
+                const double u = fma(p.Mn[0][0], fc, fma(p.Mn[0][1], fr, fma(p.Mn[0][3], d, p.Mn[0][2]))) * rw;
+                const double v = fma(p.Mn[1][0], fc, fma(p.Mn[1][1], fr, fma(p.Mn[1][3], d, p.Mn[1][2]))) * rw;
+                const double w = fma(p.Mn[2][0], fc, fma(p.Mn[2][1], fr, fma(p.Mn[2][3], d, p.Mn[2][2]))) * rw;
+                // finite position <=> valid point (aggregate_2p5d_util.py:92); non-finite ones can never pass
+                // the bounds mask of lib/proj_to_grid.py:48
+                if (fabs(u) < CUDART_INF && fabs(v) < CUDART_INF && fabs(w) < CUDART_INF) {
+                    ++n_valid;
+                    hm[i] = (float)fma(w, p.half_z, p.center_z);
+                    if (fabs(u) <= 1.0 && fabs(v) <= 1.0) {  // outside the box => outside the grid
+                        if (fabs(w) <= 1.0) {
+                            double colf, rowf, alt;
+                            eval3<D>(pc, u, v, w, colf, rowf, alt);
+                            const double cfl = floor(colf), rfl = floor(rowf);  // lib/proj_to_grid.py:42-43
+                            if (cfl >= 0.0 && rfl >= 0.0 && cfl < (double)p.xsize && rfl < (double)p.ysize) {
+                                ++n_ingrid;
+                                const double fcx = colf - cfl, frx = rowf - rfl;
+                                if (fcx < p.eps || fcx > 1.0 - p.eps || frx < p.eps || frx > 1.0 - p.eps) ++n_amb;
+                                const int cell = (int)rfl * p.xsize + (int)cfl;
+                                const uint32_t key = vs_key32((float)alt);
+                                if (cell == pend_cell) {
+                                    pend_key = max(pend_key, key);
+                                } else {
+                                    if (pend_cell >= 0) atomicMax(keygrid + pend_cell, pend_key);
+                                    pend_cell = cell;
+                                    pend_key = key;
+                                }
+                            }
+                        } else {
+                            ++n_exact;  // handled by k_unproject_scatter_exact
+                        }
+                    }
+                }
+            }
+            if (++col == p.W) {
+                col = 0;
+                ++row;
+            }
+        }
+        if (pend_cell >= 0) atomicMax(keygrid + pend_cell, pend_key);
+        if (height_map != nullptr) {
+            if (base + 3 < n_pix) {
+                *reinterpret_cast<float4*>(height_map + base) = make_float4(hm[0], hm[1], hm[2], hm[3]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (base + i < n_pix) height_map[base + i] = hm[i];
+            }
+        }
+    }
+    flush_stats(stats, n_valid, n_ingrid, n_amb, n_exact);
+}
+
+// Slow path: exact chain per pixel.  all_pixels != 0 when the polynomial is disabled.
+__global__ void __launch_bounds__(kThreads)
+k_unproject_scatter_exact(RasterParams p, VsEllipsoidConsts c, VsGeoParams g, double center_x, double half_x,
+                          double center_y, double half_y, int all_pixels, const float* __restrict__ depth,
+                          uint32_t* __restrict__ keygrid, float* __restrict__ height_map,
+                          unsigned long long* __restrict__ stats) {
+    if (!all_pixels && stats[VS_STAT_EXACT] == 0) return;
+    const int64_t n_pix = (int64_t)p.H * p.W;
+    unsigned n_valid = 0, n_ingrid = 0, n_amb = 0, n_exact = 0;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < n_pix;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const float df = depth[idx];
+        if (all_pixels && height_map != nullptr) height_map[idx] = CUDART_NAN_F;
+        if (!(df > 0.0f)) continue;
+        const int row = (int)(idx / p.W);
+        const int col = (int)(idx - (int64_t)row * p.W);
+        const double d = (double)df, fc = (double)col, fr = (double)row;
+        const double hw = fma(p.M3[0], fc, fma(p.M3[1], fr, fma(p.M3[3], d, p.M3[2])));
+        const double rw = 1.0 / hw;
+        const double u = fma(p.Mn[0][0], fc, fma(p.Mn[0][1], fr, fma(p.Mn[0][3], d, p.Mn[0][2]))) * rw;
+        const double v = fma(p.Mn[1][0], fc, fma(p.Mn[1][1], fr, fma(p.Mn[1][3], d, p.Mn[1][2]))) * rw;
+        const double w = fma(p.Mn[2][0], fc, fma(p.Mn[2][1], fr, fma(p.Mn[2][3], d, p.Mn[2][2]))) * rw;
+        if (!(fabs(u) < CUDART_INF && fabs(v) < CUDART_INF && fabs(w) < CUDART_INF)) continue;
+        if (all_pixels) {
+            ++n_valid;
+            if (height_map != nullptr) height_map[idx] = (float)fma(w, p.half_z, p.center_z);
+        }
+        if (!(fabs(u) <= 1.0 && fabs(v) <= 1.0)) continue;
+        if (!all_pixels && fabs(w) <= 1.0) continue;  // K1 already scattered it
+        if (all_pixels) ++n_exact;
+        double E, N, A;
+        vs_enu_to_utm_exact(c, g, fma(u, half_x, center_x), fma(v, half_y, center_y), fma(w, p.half_z, p.center_z), E, N,
+                            A);
+        const double colf = (E - g.ul_e) / g.col_res, rowf = (g.ul_n - N) / g.row_res;
+        const double cfl = floor(colf), rfl = floor(rowf);
+        if (cfl >= 0.0 && rfl >= 0.0 && cfl < (double)p.xsize && rfl < (double)p.ysize && A == A) {
+            ++n_ingrid;
+            const double fcx = colf - cfl, frx = rowf - rfl;
+            if (fcx < p.eps || fcx > 1.0 - p.eps || frx < p.eps || frx > 1.0 - p.eps) ++n_amb;
+            atomicMax(keygrid + ((int)rfl * p.xsize + (int)cfl), vs_key32((float)A));
+        }
+    }
+    flush_stats(stats, n_valid, n_ingrid, n_amb, n_exact);
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_points_scatter(const double* __restrict__ pts, int64_t n, double xoff, double yoff, double xres, double yres,
+                 int xsize, int ysize, unsigned long long* __restrict__ keygrid, unsigned long long* __restrict__ stats) {
+    unsigned n_valid = 0, n_ingrid = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double E = pts[3 * i], N = pts[3 * i + 1], A = pts[3 * i + 2];
+        // lib/proj_to_grid.py:42-43 (row uses xresolution, col uses yresolution -- as in the reference)
+        const double rfl = floor(__ddiv_rn(__dsub_rn(yoff, N), xres));
+        const double cfl = floor(__ddiv_rn(__dsub_rn(E, xoff), yres));
+        if (A == A) ++n_valid;
+        if (rfl >= 0.0 && cfl >= 0.0 && rfl < (double)ysize && cfl < (double)xsize && A == A) {  // :48, nanmax drops NaN
+            ++n_ingrid;
+            atomicMax(keygrid + ((int64_t)rfl * xsize + (int64_t)cfl), vs_key64(A));
+        }
+    }
+    flush_stats(stats, n_valid, n_ingrid, 0, 0);
+}
+
+int persistent_grid(const vs_ctx* ctx, int64_t work_items, int per_sm) {
+    int64_t blocks = (work_items + kThreads - 1) / kThreads;
+    int64_t cap = (int64_t)ctx->sm_count * per_sm;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+}  // namespace
+
+extern "C" {
+
+int vs_unproject_rasterize(vs_ctx* ctx, const float* depth, int32_t H, int32_t W, const double* M, uint32_t* keygrid,
+                           int clear_first, float* height_map, uint64_t* stats, void* stream_) {
+    VS_REQUIRE(ctx != nullptr, "vs_unproject_rasterize: NULL context");
+    if (!ctx->aoi_set) {
+        vs_set_error("vs_unproject_rasterize: call vs_set_aoi first");
+        return VS_ERR_STATE;
+    }
+    VS_REQUIRE(H >= 0 && W >= 0, "vs_unproject_rasterize: negative image size");
+    VS_REQUIRE(M != nullptr && keygrid != nullptr, "vs_unproject_rasterize: NULL argument");
+    VS_REQUIRE(((uintptr_t)depth & 15) == 0, "vs_unproject_rasterize: depth must be 16-byte aligned");
+    VS_REQUIRE(height_map == nullptr || ((uintptr_t)height_map & 15) == 0,
+               "vs_unproject_rasterize: height_map must be 16-byte aligned");
+    VsDeviceGuard guard(ctx->device);
+    if (!guard.ok) return vs_cuda_fail(cudaGetLastError(), "cudaSetDevice");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const VsPoly& P = ctx->poly;
+    const size_t cells = (size_t)ctx->aoi.xsize * ctx->aoi.ysize;
+    if (clear_first) VS_CUDA(cudaMemsetAsync(keygrid, 0, cells * sizeof(uint32_t), stream));
+    // the slow-path kernel reads the EXACT counter, so it needs a stats buffer even if the caller has none
+    unsigned long long* d_stats = reinterpret_cast<unsigned long long*>(stats);
+    if (d_stats == nullptr) {
+        int rc = vs_ensure_scratch(ctx, 64);
+        if (rc) return rc;
+        d_stats = reinterpret_cast<unsigned long long*>(ctx->d_scratch);
+    }
+    VS_CUDA(cudaMemsetAsync(d_stats, 0, VS_NUM_STATS * sizeof(uint64_t), stream));
+    const int64_t n_pix = (int64_t)H * W;
+    if (n_pix == 0) return VS_OK;
+    VS_REQUIRE(depth != nullptr, "vs_unproject_rasterize: depth is NULL");
+
+    RasterParams p;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 4; ++j) p.Mn[i][j] = (M[4 * i + j] - P.center[i] * M[12 + j]) * P.inv_half[i];
+    for (int j = 0; j < 4; ++j) p.M3[j] = M[12 + j];
+    p.half_z = 1.0 / P.inv_half[2];
+    p.center_z = P.center[2];
+    p.eps = ctx->ambiguity_eps;
+    p.H = H;
+    p.W = W;
+    p.xsize = ctx->aoi.xsize;
+    p.ysize = ctx->aoi.ysize;
+    p.degree = P.degree;
+
+    if (P.degree > 0) {
+        PolyCoefs pc;
+        memcpy(pc.c, P.coef, sizeof(pc.c));
+        const int grid = persistent_grid(ctx, (n_pix + 3) / 4, 8);
+        switch (P.degree) {
+            case 3: k_unproject_scatter<3><<<grid, kThreads, 0, stream>>>(p, pc, depth, keygrid, height_map, d_stats); break;
+            case 4: k_unproject_scatter<4><<<grid, kThreads, 0, stream>>>(p, pc, depth, keygrid, height_map, d_stats); break;
+            case 5: k_unproject_scatter<5><<<grid, kThreads, 0, stream>>>(p, pc, depth, keygrid, height_map, d_stats); break;
+            default: vs_set_error("vs_unproject_rasterize: bad polynomial degree"); return VS_ERR_STATE;
+        }
+        VS_CHECK_LAUNCH(ctx, "k_unproject_scatter");
+    }
+    {
+        VsEllipsoidConsts c = vs_make_ellipsoid_consts();
+        const int grid = persistent_grid(ctx, n_pix, 4);
+        k_unproject_scatter_exact<<<grid, kThreads, 0, stream>>>(p, c, ctx->geo, P.center[0], 1.0 / P.inv_half[0],
+                                                                P.center[1], 1.0 / P.inv_half[1], P.degree == 0 ? 1 : 0,
+                                                                depth, keygrid, height_map, d_stats);
+        VS_CHECK_LAUNCH(ctx, "k_unproject_scatter_exact");
+    }
+    return VS_OK;
+}
+
+int vs_points_rasterize(vs_ctx* ctx, const double* points, int64_t n_points, double xoff, double yoff,
+                        double xresolution, double yresolution, int32_t xsize, int32_t ysize, uint64_t* keygrid64,
+                        int clear_first, uint64_t* stats, void* stream_) {
+    VS_REQUIRE(ctx != nullptr, "vs_points_rasterize: NULL context");
+    VS_REQUIRE(n_points >= 0, "vs_points_rasterize: negative point count");
+    VS_REQUIRE(xsize > 0 && ysize > 0, "vs_points_rasterize: grid size must be positive");
+    VS_REQUIRE(keygrid64 != nullptr, "vs_points_rasterize: keygrid is NULL");
+    VsDeviceGuard guard(ctx->device);
+    if (!guard.ok) return vs_cuda_fail(cudaGetLastError(), "cudaSetDevice");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (clear_first) VS_CUDA(cudaMemsetAsync(keygrid64, 0, (size_t)xsize * ysize * sizeof(uint64_t), stream));
+    if (stats) VS_CUDA(cudaMemsetAsync(stats, 0, VS_NUM_STATS * sizeof(uint64_t), stream));
+    if (n_points == 0) return VS_OK;
+    VS_REQUIRE(points != nullptr, "vs_points_rasterize: points is NULL");
+    const int grid = persistent_grid(ctx, n_points, 8);
+    k_points_scatter<<<grid, kThreads, 0, stream>>>(points, n_points, xoff, yoff, xresolution, yresolution, xsize, ysize,
+                                                    reinterpret_cast<unsigned long long*>(keygrid64),
+                                                    reinterpret_cast<unsigned long long*>(stats));
+    VS_CHECK_LAUNCH(ctx, "k_points_scatter");
+    return VS_OK;
+}
+
+}  // extern "C"

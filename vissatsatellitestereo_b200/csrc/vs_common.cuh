@@ -1,0 +1,114 @@
+// Shared declarations for libvissat_b200 (sm_100a).  Internal header; the public ABI is include/vissat_b200.h.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/vissat_b200.h"
+
+#define VS_MAX_DEGREE 5
+#define VS_MAX_TERMS 56  // C(5+3,3)
+
+// ENU -> (fractional col, fractional row, altitude) polynomial in box-normalised coordinates
+// p = ((x,y,z) - center) / half, |p_i| <= 1 inside the validated box.  Terms are ordered by
+// (i, j, k) lexicographic with i + j + k <= degree (see poly_term_order()).
+struct VsPoly {
+    int degree;  // 0 = exact chain only
+    int n_terms;
+    double center[3];
+    double inv_half[3];
+    double coef[3][VS_MAX_TERMS];  // [0] = col_f, [1] = row_f, [2] = alt
+};
+
+struct VsGeoParams {
+    double lat0, lon0, alt0;
+    // precomputed for the exact chain (pymap3d order of operations)
+    double sin_lat0, cos_lat0, sin_lon0, cos_lon0;
+    double x0, y0, z0;  // ECEF of the ENU origin
+    double lam0;        // UTM central meridian (rad)
+    double north_off;   // 0 or 1e7
+    double ul_e, ul_n, row_res, col_res;
+    int xsize, ysize;
+};
+
+struct vs_ctx {
+    int device;
+    bool aoi_set;
+    vs_aoi aoi;
+    VsGeoParams geo;
+    VsPoly poly;
+    vs_fit_info fit;
+    double ambiguity_eps;
+    uint64_t launches;
+    int sm_count;
+    // small device scratch for setup-time evaluations
+    double* d_scratch;
+    size_t scratch_doubles;
+};
+
+void vs_set_error(const std::string& msg);
+int vs_cuda_fail(cudaError_t e, const char* what);
+
+#define VS_CUDA(call)                                          \
+    do {                                                       \
+        cudaError_t e__ = (call);                              \
+        if (e__ != cudaSuccess) return vs_cuda_fail(e__, #call); \
+    } while (0)
+
+#define VS_CHECK_LAUNCH(ctx, name)                                 \
+    do {                                                           \
+        cudaError_t e__ = cudaGetLastError();                      \
+        if (e__ != cudaSuccess) return vs_cuda_fail(e__, name);    \
+        (ctx)->launches++;                                         \
+    } while (0)
+
+#define VS_REQUIRE(cond, msg)           \
+    do {                                \
+        if (!(cond)) {                  \
+            vs_set_error(msg);          \
+            return VS_ERR_INVALID;      \
+        }                               \
+    } while (0)
+
+struct VsDeviceGuard {
+    int prev;
+    bool ok;
+    explicit VsDeviceGuard(int dev) : prev(-1), ok(false) {
+        if (cudaGetDevice(&prev) != cudaSuccess) return;
+        ok = (prev == dev) || (cudaSetDevice(dev) == cudaSuccess);
+        if (prev == dev) prev = -1;
+    }
+    ~VsDeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// ---- order-preserving keys ------------------------------------------------------------------------------
+// key(a) < key(b)  <=>  a < b for non-NaN floats; 0 is reserved for "empty" (it is the image of a negative
+// NaN, which never occurs: altitudes entering the scatter are finite).
+__host__ __device__ __forceinline__ uint32_t vs_key32(float f) {
+#ifdef __CUDA_ARCH__
+    uint32_t b = __float_as_uint(f);
+#else
+    union { float f; uint32_t u; } c; c.f = f; uint32_t b = c.u;
+#endif
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float vs_unkey32(uint32_t k) {
+    // k == 0 -> NaN (empty cell)
+    uint32_t b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+    return __uint_as_float(b);  // k==0 -> 0xffffffff = NaN
+}
+__device__ __forceinline__ unsigned long long vs_key64(double d) {
+    unsigned long long b = (unsigned long long)__double_as_longlong(d);
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double vs_unkey64(unsigned long long k) {
+    unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)b);  // k==0 -> all ones = NaN
+}
+
+// host-side helpers implemented in api.cu
+int vs_ensure_scratch(vs_ctx* ctx, size_t doubles);

@@ -1,0 +1,190 @@
+"""Host-side driver of the CUDA path for ONE GPU: depth maps -> per-view DSMs -> fused DSM.
+
+torch is used for device buffers and streams only; every computation is a call into libvissat_b200.so.
+The multi-GPU driver (one process per GPU) is in ``distributed.py``.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _native
+from ._native import lib, check
+
+DEFAULT_SIMD_LANES = 16     # cv2's float32 vector width on AVX-512 hosts; only matters for grids narrower than lanes+2
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda():
+    if not torch.cuda.is_available() or _native.device_count() == 0:
+        raise _native.VisSatError('no CUDA device: vissatsatellitestereo_b200 has no CPU fallback')
+
+
+def grid_shape(aoi_dict, e_resolution, n_resolution):
+    """produce_dsm.py:54-55."""
+    e_size = int(aoi_dict['width'] / e_resolution) + 1
+    n_size = int(aoi_dict['height'] / n_resolution) + 1
+    return e_size, n_size
+
+
+def aoi_struct(aoi_dict, e_resolution, n_resolution, e_size=None, n_size=None, alt_margin=(50.0, 100.0)):
+    """vs_aoi from aoi.json, following coordinate_system.py:45-47, produce_dsm.py:51-56 and the
+    (swapped-name) resolution use of lib/proj_to_grid.py:42-43."""
+    if e_size is None or n_size is None:
+        e_size, n_size = grid_shape(aoi_dict, e_resolution, n_resolution)
+    a = _native.vs_aoi()
+    a.lat0 = (aoi_dict['lat_min'] + aoi_dict['lat_max']) / 2.0
+    a.lon0 = (aoi_dict['lon_min'] + aoi_dict['lon_max']) / 2.0
+    a.alt0 = aoi_dict['alt_min']
+    a.zone = int(aoi_dict['zone_number'])
+    a.south = 0 if aoi_dict['hemisphere'] == 'N' else 1
+    a.ul_e = aoi_dict['ul_easting']
+    a.ul_n = aoi_dict['ul_northing']
+    a.row_res = e_resolution      # proj_to_grid(points, ul_e, ul_n, e_resolution, n_resolution, ...): rows / xresolution
+    a.col_res = n_resolution      # cols / yresolution
+    a.xsize = e_size
+    a.ysize = n_size
+    a.alt_lo = aoi_dict['alt_min'] - alt_margin[0]
+    a.alt_hi = aoi_dict['alt_max'] + alt_margin[1]
+    return a
+
+
+class DsmEngine:
+    """One AOI on one GPU.  Buffers are allocated once and reused across views."""
+
+    def __init__(self, aoi_dict, e_resolution=0.5, n_resolution=0.5, device=None, max_degree=5,
+                 simd_lanes=DEFAULT_SIMD_LANES, ambiguity_eps=1e-7):
+        require_cuda()
+        self.device = torch.device('cuda', torch.cuda.current_device() if device is None else device) \
+            if not isinstance(device, torch.device) else device
+        self.aoi_dict = dict(aoi_dict)
+        self.e_resolution, self.n_resolution = float(e_resolution), float(n_resolution)
+        self.e_size, self.n_size = grid_shape(aoi_dict, e_resolution, n_resolution)
+        self.simd_lanes = int(simd_lanes)
+        self.ctx = _native.Context(self.device.index)
+        self._aoi = aoi_struct(aoi_dict, e_resolution, n_resolution, self.e_size, self.n_size)
+        self.fit = self.ctx.set_aoi(self._aoi, max_degree)
+        self.ctx.set_ambiguity_eps(ambiguity_eps)
+        with torch.cuda.device(self.device):
+            self.keygrid = torch.empty((self.n_size, self.e_size), dtype=torch.int32, device=self.device)
+            self._stats = torch.zeros(_native.VS_NUM_STATS, dtype=torch.int64, device=self.device)
+            self._nan_count = torch.zeros(1, dtype=torch.int64, device=self.device)
+
+    # ---- stage A + B -------------------------------------------------------------------------------------
+    def rasterize(self, depth, inv_proj_mat, height_map=None, clear=True):
+        """aggregate_2p5d_util.py:75-98 + lib/proj_to_grid.py:42-61 -> self.keygrid (device)."""
+        assert depth.is_cuda and depth.dtype == torch.float32 and depth.dim() == 2 and depth.is_contiguous()
+        M = np.ascontiguousarray(np.asarray(inv_proj_mat, dtype=np.float64).reshape(16))
+        H, W = depth.shape
+        check(lib.vs_unproject_rasterize(self.ctx.handle, _ptr(depth), H, W, M.ctypes.data_as(C.POINTER(C.c_double)),
+                                         _ptr(self.keygrid), 1 if clear else 0, _ptr(height_map), _ptr(self._stats),
+                                         _stream(self.device)), 'vs_unproject_rasterize')
+
+    def finalize(self, out=None, count_nan=False):
+        """lib/proj_to_grid.py:62-79 + produce_dsm.py:58 -> float32 (n_size, e_size) per-view DSM (device)."""
+        if out is None:
+            out = torch.empty((self.n_size, self.e_size), dtype=torch.float32, device=self.device)
+        assert out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and \
+            tuple(out.shape) == (self.n_size, self.e_size)
+        check(lib.vs_grid_finalize(self.ctx.handle, _ptr(self.keygrid), self.e_size, self.n_size, _ptr(out),
+                                   self.simd_lanes, _ptr(self._nan_count) if count_nan else C.c_void_p(0),
+                                   _stream(self.device)), 'vs_grid_finalize')
+        return out
+
+    def view_dsm(self, depth, inv_proj_mat, out=None, height_map=None):
+        """One view of convert_depth_map_worker (aggregate_2p5d_util.py:75-102) without file I/O."""
+        self.rasterize(depth, inv_proj_mat, height_map=height_map)
+        return self.finalize(out=out)
+
+    def stats(self):
+        """Counters of the last rasterize call (synchronises)."""
+        s = self._stats.cpu().numpy()
+        return {'valid': int(s[0]), 'in_grid': int(s[1]), 'ambiguous': int(s[2]), 'exact': int(s[3])}
+
+    def last_nan_count(self):
+        return int(self._nan_count.cpu().item())
+
+    # ---- stage C ------------------------------------------------------------------------------------------
+    def fuse(self, views, out=None):
+        """aggregate_2p5d.py:65-78 on a (V, rows, W) float32 stack of per-view DSMs (device)."""
+        assert views.is_cuda and views.dtype == torch.float32 and views.dim() == 3
+        V, rows, W = views.shape
+        assert views.stride(2) == 1 and views.stride(1) == W, 'planes must be row-major contiguous'
+        if out is None:
+            out = torch.empty((rows, W), dtype=torch.float32, device=self.device)
+        check(lib.vs_fuse_views(self.ctx.handle, _ptr(views), views.stride(0), V, rows, W, _ptr(out),
+                                _stream(self.device)), 'vs_fuse_views')
+        return out
+
+    def median3x3(self, img, out=None, row_begin=0, row_end=None, in_row0=0, h_total=None, count_nan=False):
+        """aggregate_2p5d.py:81: cv2.medianBlur(float32, 3) of rows [row_begin, row_end) of an h_total-row image
+        whose rows in_row0.. are in `img`."""
+        assert img.is_cuda and img.dtype == torch.float32 and img.dim() == 2 and img.is_contiguous()
+        W = img.shape[1]
+        if h_total is None:
+            h_total = in_row0 + img.shape[0]
+        if row_end is None:
+            row_end = h_total
+        if out is None:
+            out = torch.empty((row_end - row_begin, W), dtype=torch.float32, device=self.device)
+        check(lib.vs_median3x3(self.ctx.handle, _ptr(img), in_row0, h_total, W, row_begin, row_end, _ptr(out),
+                               self.simd_lanes, _ptr(self._nan_count) if count_nan else C.c_void_p(0),
+                               _stream(self.device)), 'vs_median3x3')
+        return out
+
+    def fuse_and_blur(self, views):
+        """aggregate_2p5d.py:65-81 -> float32 (n_size, e_size) fused DSM (device)."""
+        mean = self.fuse(views)
+        return self.median3x3(mean, count_nan=True)
+
+    def launch_count(self):
+        return self.ctx.launch_count()
+
+    def close(self):
+        self.ctx.close()
+
+
+# ---- AOI-independent entry points (public proj_to_grid / converters) -----------------------------------------
+_ctx_cache = {}
+
+
+def default_context(device=None):
+    require_cuda()
+    idx = torch.cuda.current_device() if device is None else torch.device(device).index
+    if idx is None:
+        idx = torch.cuda.current_device()
+    if idx not in _ctx_cache:
+        _ctx_cache[idx] = _native.Context(idx)
+    return _ctx_cache[idx], torch.device('cuda', idx)
+
+
+def proj_to_grid_device(points, xoff, yoff, xresolution, yresolution, xsize, ysize, blur=False,
+                        simd_lanes=DEFAULT_SIMD_LANES, device=None):
+    """lib/proj_to_grid.py:41-81 on the GPU with exact float64 semantics.
+    points: (N,3) float64 (host numpy or device tensor).  Returns device float64 (ysize, xsize)
+    [, device float32 blurred grid if blur]."""
+    ctx, dev = default_context(device)
+    if not torch.is_tensor(points):
+        points = torch.from_numpy(np.ascontiguousarray(np.asarray(points, dtype=np.float64)))
+    pts = points.to(device=dev, dtype=torch.float64).contiguous()
+    assert pts.dim() == 2 and pts.shape[1] >= 3
+    if pts.shape[1] != 3:
+        pts = pts[:, :3].contiguous()
+    n = pts.shape[0]
+    keys = torch.empty((ysize, xsize), dtype=torch.int64, device=dev)
+    filled = torch.empty((ysize, xsize), dtype=torch.float64, device=dev)
+    blurred = torch.empty((ysize, xsize), dtype=torch.float32, device=dev) if blur else None
+    st = _stream(dev)
+    check(lib.vs_points_rasterize(ctx.handle, _ptr(pts), n, float(xoff), float(yoff), float(xresolution),
+                                  float(yresolution), int(xsize), int(ysize), _ptr(keys), 1, C.c_void_p(0), st),
+          'vs_points_rasterize')
+    check(lib.vs_grid_finalize64(ctx.handle, _ptr(keys), int(xsize), int(ysize), _ptr(filled), _ptr(blurred),
+                                 int(simd_lanes), st), 'vs_grid_finalize64')
+    return (filled, blurred) if blur else filled
