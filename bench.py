@@ -1,0 +1,396 @@
+#!/usr/bin/env python
+"""bench.py -- depth Mpix/s -> fused DSM (BASELINE.json metric) for the B200 path and the CPU reference arm.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config C2] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+           bench.py --gpus N --steps K --warmup W
+
+One "step" = one pass of the whole hot path over one batch of synthetic views: every view through stage A
+(unproject + geodesy + scatter-max) and stage B (hole fill + 3x3 median) into a per-view DSM, then stage C
+(robust cross-view fusion + 3x3 median) into the fused DSM.  At N = 1 the workload is BASELINE.json configs[1]
+(C2: 50 views x 2048^2 depth, 2048^2 grid @ 0.3 m).  At N > 1 every rank processes its own C2-sized block of views
+(weak scaling: 50*N views in total), the per-view DSM row bands are exchanged with one NCCL all-to-all and every
+rank fuses its own band of grid rows.
+
+`value`  : Mpix/s with the depth maps already resident in HBM (device -> device).
+`e2e`    : same metric through the host-buffer entry point (pinned host depth maps -> H2D -> kernels -> D2H of
+           every per-view DSM and of the fused DSM).
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+METRIC = 'depth_mpix_per_s_to_fused_dsm'
+UNIT = 'Mpix/s'
+
+
+def load_peaks():
+    path = os.path.join(REPO, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as fp:
+            return float(json.load(fp)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(prefix='clocks_', suffix='.csv')
+            os.close(fd)
+            self.fp = open(self.path, 'w')
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=self.fp, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.fp.close()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        with open(self.path) as fp:
+            for line in fp:
+                t = [x.strip() for x in line.split(',')]
+                if len(t) < 9:
+                    continue
+                try:
+                    sm.append(float(t[1]))
+                    smax.append(float(t[2]))
+                    power.append(float(t[3]))
+                except ValueError:
+                    continue
+                for name, val in zip(names, t[5:9]):
+                    if val.lower().startswith('active'):
+                        reasons.add(name)
+        os.unlink(self.path)
+        if sm:
+            # "under load": samples in the upper half of the observed power range
+            p = np.array(power)
+            load = p >= (p.min() + 0.5 * (p.max() - p.min())) if p.max() > p.min() else np.ones(len(p), bool)
+            out = {'sm_mhz': float(np.median(np.array(sm)[load])), 'sm_max_mhz': float(max(smax)),
+                   'reasons': sorted(reasons), 'samples': len(sm), 'power_w_max': float(p.max())}
+        return out
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def _cpu_view_worker(args):
+    from oracle import pipeline as op
+    depth, M, aoi, res = args
+    dsm, _ = op.convert_depth_map(depth, M, aoi, res, res, fast=False)     # faithful: Python hole-fill loop
+    return dsm
+
+
+def cpu_sample(cfg, n_views, band_rows, cores, geo=None):
+    """Time the oracle (CPU restatement of the reference) on a bounded sample of the workload and extrapolate
+    linearly to the whole config: n_views views through the per-view stage with a
+    multiprocessing.Pool(cores) exactly like aggregate_2p5d_util.py:138-146, then the single-process fusion
+    (aggregate_2p5d.py:65-81) on band_rows grid rows of a V-view cube."""
+    import multiprocessing as mp
+    from oracle import geodesy, pipeline as op
+    from vissatsatellitestereo_b200 import synthetic as S
+    scene = S.make_scene(cfg, geodesy, device='cpu', views=range(n_views))
+    jobs = [(d.numpy(), M, scene.aoi, cfg.res) for d, M in zip(scene.depths, scene.mats)]
+    t0 = time.perf_counter()
+    with mp.get_context('fork').Pool(min(cores, n_views)) as pool:
+        dsms = pool.map(_cpu_view_worker, jobs, chunksize=1)
+    t_views = time.perf_counter() - t0
+    t_fuse = 0.0
+    if cfg.fuse:
+        band_rows = min(band_rows, dsms[0].shape[0])
+        cube = [dsms[v % n_views][:band_rows].copy() for v in range(cfg.n_views)]
+        t0 = time.perf_counter()
+        op.fuse_dsms(cube)
+        t_fuse = time.perf_counter() - t0
+    n_rows = dsms[0].shape[0]
+    total = t_views * (cfg.n_views / n_views) + t_fuse * (n_rows / max(band_rows, 1))
+    mpix = cfg.n_views * cfg.height * cfg.width / 1e6
+    return {'value': mpix / total, 't_views_s': t_views, 't_fuse_s': t_fuse, 'extrapolated_total_s': total,
+            'sample': '{} of {} views through the per-view stage (Pool({})), fusion on {} of {} grid rows x {} views; '
+                      'extrapolated linearly'.format(n_views, cfg.n_views, min(cores, n_views), band_rows, n_rows,
+                                                     cfg.n_views)}
+
+
+def run_reference_arm(args, cfg):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_views = max(1, min(cores, cfg.n_views, 16))
+    vals, last = [], None
+    for i in range(args.warmup + args.steps):
+        last = cpu_sample(cfg, n_views, 32, cores)
+        if i >= args.warmup:
+            vals.append(last['value'])
+    value = float(np.mean(vals))
+    mpix = cfg.n_views * cfg.height * cfg.width / 1e6
+    line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * mpix / value,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': workload_config(cfg, 1),
+            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': min(cores, n_views), 'kind': 'port',
+                             'sample': last['sample'], 'host_cpu_count': cores},
+            'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line))
+
+
+def workload_config(cfg, n_gpus):
+    return {'workload': '{}: {} views x {}x{} float32 depth per GPU -> {}x{} grid @ {} m ({})'.format(
+        cfg.name, cfg.n_views, cfg.height, cfg.width, cfg.n_size, cfg.e_size, cfg.res,
+        'BASELINE.json configs[1]' if cfg.name == 'C2' else 'BASELINE.json config'),
+        'views_per_gpu': cfg.n_views, 'views_total': cfg.n_views * n_gpus,
+        'depth_hw': [cfg.height, cfg.width], 'grid_hw': [cfg.n_size, cfg.e_size], 'resolution_m': cfg.res,
+        'fuse': cfg.fuse, 'parallelism': 'views sharded over {} GPU(s); fusion by grid-row band'.format(n_gpus),
+        'cache': 'inputs: {:.0f} MB of depth per GPU per step (> 126 MB L2 for C2..C5); no explicit flush'.format(
+            cfg.n_views * cfg.height * cfg.width * 4 / 1e6)}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_b200_arm(args, cfg):
+    import torch
+    import torch.distributed as dist
+    from vissatsatellitestereo_b200 import engine as E, synthetic as S, distributed as D
+    from vissatsatellitestereo_b200.lib import latlon_utm_converter as geo
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    E.require_cuda()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    assert world == args.gpus, 'launch with torchrun --nproc-per-node {} (WORLD_SIZE={})'.format(args.gpus, world)
+
+    # ---- synthetic inputs, generated on the device (untimed).  Rank r holds views [r*V, (r+1)*V) of the job.
+    V = cfg.n_views
+    job = S.SynthConfig(**cfg.__dict__)
+    job.n_views = V * world
+    aoi = S.make_aoi(job, geo)
+    terrain = S.Terrain(job, device=dev)
+    mats, depths = [], []
+    for v in range(rank * V, (rank + 1) * V):
+        M, _ = S.make_camera(job, v, aoi['alt_min'])
+        mats.append(M)
+        depths.append(S.make_depth_map(job, v, M, terrain, device=dev))
+    del terrain
+    torch.cuda.synchronize()
+
+    eng = E.DsmEngine(aoi, cfg.res, cfg.res, device=dev)
+    eng.collect_stats = False
+    stack = torch.empty((V, eng.n_size, eng.e_size), dtype=torch.float32, device=dev)
+    view_counts = [V] * world
+    P = cfg.height * cfg.width
+    G = eng.n_size * eng.e_size
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    stage_events = []
+
+    def step(record):
+        evs = []
+        for v in range(V):
+            eng.clear_keygrid()
+            if record:
+                a, b, c = ev(), ev(), ev()
+                a.record()
+            eng.rasterize(depths[v], mats[v], clear=False)
+            if record:
+                b.record()
+            eng.finalize(out=stack[v])
+            if record:
+                c.record()
+                evs.append((a, b, c))
+        fe = None
+        if cfg.fuse:
+            if record:
+                f0, f1, f2 = ev(), ev(), ev()
+                f0.record()
+            if world == 1:
+                mean = eng.fuse(stack)
+                if record:
+                    f1.record()
+                fused = eng.median3x3(mean, count_nan=True)
+            else:
+                fused, _ = D.fuse_distributed(eng, stack, view_counts)
+                if record:
+                    f1.record()
+            if record:
+                f2.record()
+                fe = (f0, f1, f2)
+        else:
+            fused = None
+        if record:
+            stage_events.append((evs, fe))
+        return fused
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(False)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.launch_count()
+    t0, t1 = ev(), ev()
+    barrier()
+    t0.record()
+    for _ in range(args.steps):
+        fused = step(True)
+    t1.record()
+    barrier()
+    launches = eng.launch_count() - launches0
+    ms_total = t0.elapsed_time(t1)
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    mpix_step = V * world * P / 1e6
+    value = mpix_step / (ms_step * 1e-3)
+
+    # per-stage device times inside the timed region
+    k1 = np.array([a.elapsed_time(b) for evs, _ in stage_events for (a, b, c) in evs])
+    k2 = np.array([b.elapsed_time(c) for evs, _ in stage_events for (a, b, c) in evs])
+    fuse_ms = np.array([fe[0].elapsed_time(fe[1]) for _, fe in stage_events if fe]) if cfg.fuse else np.array([0.0])
+    blur_ms = np.array([fe[1].elapsed_time(fe[2]) for _, fe in stage_events if fe]) if cfg.fuse else np.array([0.0])
+    stages = {'k1_unproject_scatter_ms_per_view': float(k1.mean()), 'k2_grid_finalize_ms_per_view': float(k2.mean()),
+              'k3_fuse_ms_per_step' if world == 1 else 'exchange_plus_fuse_ms_per_step': float(fuse_ms.mean()),
+              'k4_median3x3_ms_per_step' if world == 1 else 'tail_ms_per_step': float(blur_ms.mean()),
+              'share_of_step': {'k1': float(k1.sum() / ms_total), 'k2': float(k2.sum() / ms_total),
+                                'fuse': float(fuse_ms.sum() / ms_total), 'blur': float(blur_ms.sum() / ms_total)}}
+
+    # ---- e2e: pinned host depth maps -> H2D -> kernels -> D2H of per-view DSMs + fused DSM, every step
+    e2e = None
+    clocks = sampler.stop() if rank == 0 else None
+    if world == 1:
+        host_depths = [d.cpu().pin_memory() for d in depths]
+        host_views = torch.empty((V, eng.n_size, eng.e_size), dtype=torch.float32).pin_memory()
+        host_fused = torch.empty((eng.n_size, eng.e_size), dtype=torch.float32).pin_memory()
+        for _ in range(max(1, min(args.warmup, 2))):
+            eng.process_host(host_depths, mats, host_views, host_fused, stack=stack, fuse=cfg.fuse)
+        n_e2e = max(1, min(args.steps, 5))
+        torch.cuda.synchronize()
+        w0 = time.perf_counter()
+        e0, e1 = ev(), ev()
+        e0.record()
+        for _ in range(n_e2e):
+            eng.process_host(host_depths, mats, host_views, host_fused, stack=stack, fuse=cfg.fuse)
+        e1.record()
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - w0) / n_e2e
+        dev_ms = e0.elapsed_time(e1) / n_e2e
+        t_e2e = max(wall, dev_ms * 1e-3)
+        e2e = {'value': mpix_step / t_e2e, 'unit': UNIT, 'h2d_bytes_per_step': int(V * P * 4),
+               'd2h_bytes_per_step': int(V * G * 4 + (G * 4 if cfg.fuse else 0)), 'ms_per_step': 1e3 * t_e2e,
+               'steps': n_e2e, 'api': 'DsmEngine.process_host (pinned host buffers in/out, 3 streams)'}
+        if cfg.fuse:
+            assert np.array_equal(host_fused.numpy(), fused.cpu().numpy(), equal_nan=True), 'e2e result differs'
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = load_peaks()
+    # dominant kernel and its roofline (algorithmic bytes per launch / measured launch duration)
+    per_step = {'k1': k1.mean() * V, 'k2': k2.mean() * V, 'fuse': fuse_ms.mean(), 'blur': blur_ms.mean()}
+    alg = {'k1': (4.0 * P, k1.mean(), 'k_unproject_scatter: 4 B/pixel depth read'),
+           'k2': (8.0 * G, k2.mean(), 'k_grid_finalize: 4 B/cell key read + 4 B/cell DSM write'),
+           'fuse': (4.0 * G * V * world / world + 4.0 * G / world, fuse_ms.mean(),
+                    'k_fuse: 4 B/cell/view read + 4 B/cell write'),
+           'blur': (8.0 * G / world, blur_ms.mean(), 'k_median3x3: 4 B read + 4 B write per cell')}
+    top = max(per_step, key=per_step.get)
+    if world > 1 and top in ('fuse', 'blur'):
+        top = 'k1' if per_step['k1'] >= per_step['k2'] else 'k2'      # exchange time is not a kernel roofline
+    bytes_launch, ms_launch, what = alg[top]
+    achieved = bytes_launch / (ms_launch * 1e-3) / 1e9
+    roofline = {'bound': 'hbm', 'kernel': what, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+                'algorithmic_bytes_per_launch': bytes_launch, 'avg_launch_ms': float(ms_launch),
+                'all_kernels_gbs': {k: float(alg[k][0] / (alg[k][1] * 1e-3) / 1e9) for k in alg if alg[k][1] > 0}}
+    traffic_file = os.path.join(REPO, 'profiles', 'traffic.json')
+    if os.path.exists(traffic_file):
+        try:
+            with open(traffic_file) as fp:
+                roofline['traffic'] = json.load(fp).get(top)
+        except Exception:
+            pass
+    # whole-pipeline algorithmic bytes (SURVEY.md §8d B_alg) for context
+    b_alg = V * world * 4.0 * P + V * world * 4.0 * G + (V * world * 4.0 * G + 4.0 * G if cfg.fuse else 0.0)
+    pipeline_gbs = b_alg / (ms_step * 1e-3) / 1e9
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        r = cpu_sample(cfg, max(1, min(cores, cfg.n_views, 16)), 32, cores)
+        cpu = {'value': r['value'], 'unit': UNIT, 'cores': min(cores, 16, cfg.n_views), 'kind': 'port',
+               'sample': r['sample'], 'host_cpu_count': cores}
+
+    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': workload_config(cfg, world),
+            'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline,
+            'cpu_baseline': cpu, 'stages': stages,
+            'pipeline': {'algorithmic_bytes_per_step': b_alg, 'achieved_gbs': pipeline_gbs,
+                         'frac_of_hbm_peak': pipeline_gbs / (peak * world)},
+            'fit': eng.fit}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--config', default='C2')
+    ap.add_argument('--views', type=int, default=None, help='override views per GPU (debugging)')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    from vissatsatellitestereo_b200 import synthetic as S
+    cfg = S.SynthConfig(**S.CONFIGS[args.config].__dict__)
+    if args.views:
+        cfg.n_views = args.views
+    if args.impl == 'reference':
+        run_reference_arm(args, cfg)
+    else:
+        run_b200_arm(args, cfg)
+
+
+if __name__ == '__main__':
+    main()

@@ -104,6 +104,10 @@ int vs_set_ambiguity_eps(vs_ctx* ctx, double eps_cells); /* default 1e-7 */
 int vs_unproject_rasterize(vs_ctx* ctx, const float* depth, int32_t H, int32_t W, const double* inv_proj_mat,
                            uint32_t* keygrid, int clear_first, float* height_map, uint64_t* stats, void* stream);
 
+/* Reset `n_keys` 4-byte (key_bytes = 4) or 8-byte (key_bytes = 8) keys to "empty" (the NaN placeholders of
+ * lib/proj_to_grid.py:53-55).  Same effect as clear_first on the rasterisers, as a separate enqueue. */
+int vs_keygrid_clear(vs_ctx* ctx, void* keygrid, int64_t n_keys, int key_bytes, void* stream);
+
 /* lib/proj_to_grid.py:42-61 for explicit points: dev float64 N*3 rows (E, N, alt) in the grid's UTM frame.
  * Exact float64 semantics: keygrid64 holds uint64 keys of the float64 altitude (0 = empty).
  * Grid geometry is passed explicitly (this is the public proj_to_grid signature, independent of vs_set_aoi). */

@@ -62,8 +62,11 @@ def test_exact_converters_vs_oracle(eng_mod):
     assert isinstance(es, float)
     assert abs(es + 183.79014029) < 1e-6 and abs(ns + 221.86356704) < 1e-6 and abs(us - 50.30348255) < 1e-6
     # published known answers
-    E, N = C2.latlon_to_eastnorh(np.array([[56.0]]), np.array([[12.0]]))
+    # (PROJ docs: `echo 12 56 | proj +proj=utm +zone=32`; utm's zone rule would pick 33 for lon = 12)
+    from vissatsatellitestereo_b200.lib._geo_common import run2
+    E, N = run2('vs_geodetic_to_utm', np.array([[56.0]]), np.array([[12.0]]), 32, 0)
     assert abs(E[0, 0] - 687071.44) < 0.006 and abs(N[0, 0] - 6210141.33) < 0.006
+    assert C2.latlon_to_zone_number(56.0, 12.0) == 33 and C2.latlon_to_zone_number(60.0, 5.0) == 32
     # northern hemisphere + both of the reference's __main__ samples
     for s in (1, -1):
         la = np.array([[s * 47.9941214]])
@@ -207,10 +210,22 @@ def test_per_view_dsm_vs_reference_golden(golden, eng_mod, lanes, case):
         diff = np.abs(got.astype(np.float64) - want[v].astype(np.float64))
         diff[np.isnan(diff)] = 0
         assert diff[~allow].max() <= HEIGHT_TOL, 'view {} max diff {}'.format(v, diff[~allow].max())
-        n_exact_bits += int(np.sum((got == want[v]) | (np.isnan(got) & np.isnan(want[v]))))
-        n_cells += got.size
-    # the polynomial reproduces the float64 chain to ~1e-9 m, so almost every float32 height is identical
-    assert n_exact_bits / n_cells > 0.995, n_exact_bits / n_cells
+        # Bit-identical float32 heights are expected everywhere except (a) where the ~1e-9 m noise of either
+        # float64 chain crosses a float32 rounding boundary (~1e-4 of cells) and (b) hole cells filled from an
+        # EVEN number of neighbours: the reference averages the two middle float64 altitudes and then rounds,
+        # the 32-bit-key path averages the two rounded values (<= 1 ulp apart); (b) also reaches the 3x3 blur
+        # neighbourhood of such a cell.
+        _, pts = op.unproject_depth(depths[v], mats[v])
+        raw = op._scatter_nanmax(op.enu_points_to_utm(pts, aoi), aoi['ul_easting'], aoi['ul_northing'], res, res,
+                                 eng.e_size, eng.n_size)
+        valid = (~np.isnan(raw)).astype(np.float32)
+        nb = cv2.filter2D(valid, -1, np.ones((3, 3), np.float32), borderType=cv2.BORDER_CONSTANT)
+        even_hole = np.isnan(raw) & (nb > 0) & (np.round(nb).astype(int) % 2 == 0)
+        even_zone = cv2.dilate(even_hole.astype(np.uint8), np.ones((3, 3), np.uint8)).astype(bool)
+        same = (got == want[v]) | (np.isnan(got) & np.isnan(want[v]))
+        n_exact_bits += int(np.sum(same[~even_zone]))
+        n_cells += int(np.sum(~even_zone))
+    assert n_exact_bits / n_cells > 0.998, n_exact_bits / n_cells
 
 
 @pytest.mark.parametrize('case', ['c1', 'c5', 'c3'])

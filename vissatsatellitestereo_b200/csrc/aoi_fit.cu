@@ -129,6 +129,23 @@ double halton(int index, int base) {
 
 }  // namespace
 
+int vs_upload_exact_params(vs_ctx* ctx) {
+    VsDeviceGuard guard(ctx->device);
+    if (!guard.ok) return vs_cuda_fail(cudaGetLastError(), "cudaSetDevice");
+    VsExactParams ex;
+    memset(&ex, 0, sizeof(ex));
+    ex.c = vs_make_ellipsoid_consts();
+    ex.g = ctx->geo;
+    for (int d = 0; d < 3; ++d) {
+        ex.center[d] = ctx->poly.center[d];
+        ex.half[d] = 1.0 / ctx->poly.inv_half[d];
+    }
+    ex.eps = ctx->ambiguity_eps;
+    if (!ctx->d_exact) VS_CUDA(cudaMalloc(&ctx->d_exact, sizeof(VsExactParams)));
+    VS_CUDA(cudaMemcpy(ctx->d_exact, &ex, sizeof(ex), cudaMemcpyHostToDevice));
+    return VS_OK;
+}
+
 extern "C" int vs_set_aoi(vs_ctx* ctx, const vs_aoi* aoi, int max_degree, vs_fit_info* info) {
     VS_REQUIRE(ctx != nullptr && aoi != nullptr, "vs_set_aoi: NULL argument");
     VS_REQUIRE(aoi->xsize > 0 && aoi->ysize > 0, "vs_set_aoi: grid size must be positive");
@@ -182,6 +199,8 @@ extern "C" int vs_set_aoi(vs_ctx* ctx, const vs_aoi* aoi, int max_degree, vs_fit
         ctx->fit.box_half[d] = half;
     }
     if (info) *info = ctx->fit;
+    rc = vs_upload_exact_params(ctx);
+    if (rc) return rc;
     if (max_degree == 0) return VS_OK;  // exact chain for every point
 
     // ---- held-out validation points (Halton), shared by all candidate degrees

@@ -133,6 +133,7 @@ int vs_ctx_create(int device, vs_ctx** out) {
     ctx->sm_count = prop.multiProcessorCount;
     ctx->d_scratch = nullptr;
     ctx->scratch_doubles = 0;
+    ctx->d_exact = nullptr;
     *out = ctx;
     return VS_OK;
 }
@@ -141,6 +142,7 @@ int vs_ctx_destroy(vs_ctx* ctx) {
     if (!ctx) return VS_OK;
     VsDeviceGuard guard(ctx->device);
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+    if (ctx->d_exact) cudaFree(ctx->d_exact);
     delete ctx;
     return VS_OK;
 }
@@ -149,6 +151,7 @@ int vs_set_ambiguity_eps(vs_ctx* ctx, double eps_cells) {
     VS_REQUIRE(ctx != nullptr, "vs_set_ambiguity_eps: ctx is NULL");
     VS_REQUIRE(eps_cells >= 0 && eps_cells < 0.5, "vs_set_ambiguity_eps: eps must be in [0, 0.5)");
     ctx->ambiguity_eps = eps_cells;
+    if (ctx->aoi_set) return vs_upload_exact_params(ctx);
     return VS_OK;
 }
 

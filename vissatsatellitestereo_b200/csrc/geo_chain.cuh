@@ -25,6 +25,15 @@ struct VsEllipsoidConsts {
 // Filled once on the host (api.cu) and passed to kernels by value.
 VsEllipsoidConsts vs_make_ellipsoid_consts();
 
+// Everything the per-point exact slow path of the fused rasteriser needs; lives in device memory
+// (vs_ctx::d_exact, uploaded by vs_set_aoi) so that the out-of-line slow path takes one pointer.
+struct VsExactParams {
+    VsEllipsoidConsts c;
+    VsGeoParams g;
+    double center[3], half[3];  // ENU box of the polynomial
+    double eps;                 // ambiguity threshold (cells)
+};
+
 // ---------------------------------------------------------------------------------------------------------
 // pymap3d
 // ---------------------------------------------------------------------------------------------------------

@@ -8,8 +8,8 @@
 //     on order-preserving float32 keys.  Consecutive pixels of one thread that fall in the same cell are
 //     merged in registers before the atomic.  Bound by the FP64 pipe and the L2 atomic units, not by HBM
 //     (4 bytes read per pixel); see DESIGN.md.
-// K1x k_unproject_scatter_exact  same scan, but only for pixels the polynomial does not cover (outside the
-//     fitted altitude range, or every pixel when the fit is disabled); exits at once when K1 counted none.
+//     Points outside the fitted altitude range take the exact chain through an out-of-line call (rare).
+// K1x k_unproject_scatter_exact  exact chain for every pixel, used only when the polynomial is disabled.
 // K1b k_points_scatter      lib/proj_to_grid.py:42-61 for explicit float64 (E,N,alt) rows, 64-bit keys.
 #include <math_constants.h>
 
@@ -67,10 +67,32 @@ __device__ __forceinline__ void flush_stats(unsigned long long* stats, unsigned 
     if (threadIdx.x < 4 && s_acc[threadIdx.x]) atomicAdd(&stats[threadIdx.x], (unsigned long long)s_acc[threadIdx.x]);
 }
 
+// Rare per-point slow path of K1 (point outside the fitted altitude range): exact chain, kept out of line and
+// fed from one device-memory parameter block so that it costs the streaming path neither registers nor a
+// stack copy of the kernel parameters.  Returns 1 if the point landed in the grid, 2 if it is also within
+// eps of a cell edge.
+__device__ __noinline__ int scatter_exact_point(const VsExactParams* __restrict__ ex, double u, double v, double w,
+                                                uint32_t* __restrict__ keygrid) {
+    double E, N, A;
+    const VsGeoParams& g = ex->g;
+    vs_enu_to_utm_exact(ex->c, g, fma(u, ex->half[0], ex->center[0]), fma(v, ex->half[1], ex->center[1]),
+                        fma(w, ex->half[2], ex->center[2]), E, N, A);
+    const double colf = (E - g.ul_e) / g.col_res, rowf = (g.ul_n - N) / g.row_res;
+    const double cfl = floor(colf), rfl = floor(rowf);
+    if (cfl >= 0.0 && rfl >= 0.0 && cfl < (double)g.xsize && rfl < (double)g.ysize && A == A) {
+        atomicMax(keygrid + ((int)rfl * g.xsize + (int)cfl), vs_key32((float)A));
+        const double fcx = colf - cfl, frx = rowf - rfl;
+        const double eps = ex->eps;
+        return (fcx < eps || fcx > 1.0 - eps || frx < eps || frx > 1.0 - eps) ? 2 : 1;
+    }
+    return 0;
+}
+
 template <int D>
-__global__ void __launch_bounds__(kThreads)
-k_unproject_scatter(RasterParams p, PolyCoefs pc, const float* __restrict__ depth, uint32_t* __restrict__ keygrid,
-                    float* __restrict__ height_map, unsigned long long* __restrict__ stats) {
+__global__ void __launch_bounds__(kThreads, 3)
+k_unproject_scatter(RasterParams p, PolyCoefs pc, const VsExactParams* __restrict__ ex, const float* __restrict__ depth,
+                    uint32_t* __restrict__ keygrid, float* __restrict__ height_map,
+                    unsigned long long* __restrict__ stats) {
     const int64_t n_pix = (int64_t)p.H * p.W;
     const int64_t n_chunks = (n_pix + 3) >> 2;
     unsigned n_valid = 0, n_ingrid = 0, n_amb = 0, n_exact = 0;
@@ -129,7 +151,10 @@ k_unproject_scatter(RasterParams p, PolyCoefs pc, const float* __restrict__ dept
                                 }
                             }
                         } else {
-                            ++n_exact;  // handled by k_unproject_scatter_exact
+                            ++n_exact;
+                            const int r = scatter_exact_point(ex, u, v, w, keygrid);
+                            n_ingrid += (r != 0);
+                            n_amb += (r == 2);
                         }
                     }
                 }
@@ -153,13 +178,13 @@ k_unproject_scatter(RasterParams p, PolyCoefs pc, const float* __restrict__ dept
     flush_stats(stats, n_valid, n_ingrid, n_amb, n_exact);
 }
 
-// Slow path: exact chain per pixel.  all_pixels != 0 when the polynomial is disabled.
+// Exact chain for every pixel (polynomial disabled: vs_set_aoi(max_degree = 0) or a fit that failed validation).
 __global__ void __launch_bounds__(kThreads)
 k_unproject_scatter_exact(RasterParams p, VsEllipsoidConsts c, VsGeoParams g, double center_x, double half_x,
-                          double center_y, double half_y, int all_pixels, const float* __restrict__ depth,
+                          double center_y, double half_y, const float* __restrict__ depth,
                           uint32_t* __restrict__ keygrid, float* __restrict__ height_map,
                           unsigned long long* __restrict__ stats) {
-    if (!all_pixels && stats[VS_STAT_EXACT] == 0) return;
+    const bool all_pixels = true;
     const int64_t n_pix = (int64_t)p.H * p.W;
     unsigned n_valid = 0, n_ingrid = 0, n_amb = 0, n_exact = 0;
     for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < n_pix;
@@ -181,8 +206,7 @@ k_unproject_scatter_exact(RasterParams p, VsEllipsoidConsts c, VsGeoParams g, do
             if (height_map != nullptr) height_map[idx] = (float)fma(w, p.half_z, p.center_z);
         }
         if (!(fabs(u) <= 1.0 && fabs(v) <= 1.0)) continue;
-        if (!all_pixels && fabs(w) <= 1.0) continue;  // K1 already scattered it
-        if (all_pixels) ++n_exact;
+        ++n_exact;
         double E, N, A;
         vs_enu_to_utm_exact(c, g, fma(u, half_x, center_x), fma(v, half_y, center_y), fma(w, p.half_z, p.center_z), E, N,
                             A);
@@ -246,14 +270,8 @@ int vs_unproject_rasterize(vs_ctx* ctx, const float* depth, int32_t H, int32_t W
     const VsPoly& P = ctx->poly;
     const size_t cells = (size_t)ctx->aoi.xsize * ctx->aoi.ysize;
     if (clear_first) VS_CUDA(cudaMemsetAsync(keygrid, 0, cells * sizeof(uint32_t), stream));
-    // the slow-path kernel reads the EXACT counter, so it needs a stats buffer even if the caller has none
     unsigned long long* d_stats = reinterpret_cast<unsigned long long*>(stats);
-    if (d_stats == nullptr) {
-        int rc = vs_ensure_scratch(ctx, 64);
-        if (rc) return rc;
-        d_stats = reinterpret_cast<unsigned long long*>(ctx->d_scratch);
-    }
-    VS_CUDA(cudaMemsetAsync(d_stats, 0, VS_NUM_STATS * sizeof(uint64_t), stream));
+    if (d_stats) VS_CUDA(cudaMemsetAsync(d_stats, 0, VS_NUM_STATS * sizeof(uint64_t), stream));
     const int64_t n_pix = (int64_t)H * W;
     if (n_pix == 0) return VS_OK;
     VS_REQUIRE(depth != nullptr, "vs_unproject_rasterize: depth is NULL");
@@ -271,26 +289,37 @@ int vs_unproject_rasterize(vs_ctx* ctx, const float* depth, int32_t H, int32_t W
     p.ysize = ctx->aoi.ysize;
     p.degree = P.degree;
 
+    VsEllipsoidConsts c = vs_make_ellipsoid_consts();
     if (P.degree > 0) {
         PolyCoefs pc;
         memcpy(pc.c, P.coef, sizeof(pc.c));
+        const VsExactParams* ex = reinterpret_cast<const VsExactParams*>(ctx->d_exact);
         const int grid = persistent_grid(ctx, (n_pix + 3) / 4, 8);
         switch (P.degree) {
-            case 3: k_unproject_scatter<3><<<grid, kThreads, 0, stream>>>(p, pc, depth, keygrid, height_map, d_stats); break;
-            case 4: k_unproject_scatter<4><<<grid, kThreads, 0, stream>>>(p, pc, depth, keygrid, height_map, d_stats); break;
-            case 5: k_unproject_scatter<5><<<grid, kThreads, 0, stream>>>(p, pc, depth, keygrid, height_map, d_stats); break;
+            case 3: k_unproject_scatter<3><<<grid, kThreads, 0, stream>>>(p, pc, ex, depth, keygrid, height_map, d_stats); break;
+            case 4: k_unproject_scatter<4><<<grid, kThreads, 0, stream>>>(p, pc, ex, depth, keygrid, height_map, d_stats); break;
+            case 5: k_unproject_scatter<5><<<grid, kThreads, 0, stream>>>(p, pc, ex, depth, keygrid, height_map, d_stats); break;
             default: vs_set_error("vs_unproject_rasterize: bad polynomial degree"); return VS_ERR_STATE;
         }
         VS_CHECK_LAUNCH(ctx, "k_unproject_scatter");
-    }
-    {
-        VsEllipsoidConsts c = vs_make_ellipsoid_consts();
+    } else {
         const int grid = persistent_grid(ctx, n_pix, 4);
         k_unproject_scatter_exact<<<grid, kThreads, 0, stream>>>(p, c, ctx->geo, P.center[0], 1.0 / P.inv_half[0],
-                                                                P.center[1], 1.0 / P.inv_half[1], P.degree == 0 ? 1 : 0,
-                                                                depth, keygrid, height_map, d_stats);
+                                                                P.center[1], 1.0 / P.inv_half[1], depth, keygrid,
+                                                                height_map, d_stats);
         VS_CHECK_LAUNCH(ctx, "k_unproject_scatter_exact");
     }
+    return VS_OK;
+}
+
+int vs_keygrid_clear(vs_ctx* ctx, void* keygrid, int64_t n_keys, int key_bytes, void* stream_) {
+    VS_REQUIRE(ctx != nullptr, "vs_keygrid_clear: NULL context");
+    VS_REQUIRE(n_keys >= 0 && (key_bytes == 4 || key_bytes == 8), "vs_keygrid_clear: bad size");
+    if (n_keys == 0) return VS_OK;
+    VS_REQUIRE(keygrid != nullptr, "vs_keygrid_clear: NULL keygrid");
+    VsDeviceGuard guard(ctx->device);
+    if (!guard.ok) return vs_cuda_fail(cudaGetLastError(), "cudaSetDevice");
+    VS_CUDA(cudaMemsetAsync(keygrid, 0, (size_t)n_keys * key_bytes, (cudaStream_t)stream_));
     return VS_OK;
 }
 

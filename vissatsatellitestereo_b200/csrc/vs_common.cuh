@@ -46,6 +46,7 @@ struct vs_ctx {
     // small device scratch for setup-time evaluations
     double* d_scratch;
     size_t scratch_doubles;
+    void* d_exact;  // VsExactParams on the device (geo_chain.cuh)
 };
 
 void vs_set_error(const std::string& msg);
@@ -112,3 +113,4 @@ __device__ __forceinline__ double vs_unkey64(unsigned long long k) {
 
 // host-side helpers implemented in api.cu
 int vs_ensure_scratch(vs_ctx* ctx, size_t doubles);
+int vs_upload_exact_params(vs_ctx* ctx);  // aoi_fit.cu

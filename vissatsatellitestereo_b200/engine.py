@@ -68,6 +68,7 @@ class DsmEngine:
         self.e_resolution, self.n_resolution = float(e_resolution), float(n_resolution)
         self.e_size, self.n_size = grid_shape(aoi_dict, e_resolution, n_resolution)
         self.simd_lanes = int(simd_lanes)
+        self.collect_stats = True      # per-view counters (valid / in-grid / ambiguous / exact); one 32-byte memset
         self.ctx = _native.Context(self.device.index)
         self._aoi = aoi_struct(aoi_dict, e_resolution, n_resolution, self.e_size, self.n_size)
         self.fit = self.ctx.set_aoi(self._aoi, max_degree)
@@ -84,8 +85,13 @@ class DsmEngine:
         M = np.ascontiguousarray(np.asarray(inv_proj_mat, dtype=np.float64).reshape(16))
         H, W = depth.shape
         check(lib.vs_unproject_rasterize(self.ctx.handle, _ptr(depth), H, W, M.ctypes.data_as(C.POINTER(C.c_double)),
-                                         _ptr(self.keygrid), 1 if clear else 0, _ptr(height_map), _ptr(self._stats),
+                                         _ptr(self.keygrid), 1 if clear else 0, _ptr(height_map),
+                                         _ptr(self._stats) if self.collect_stats else C.c_void_p(0),
                                          _stream(self.device)), 'vs_unproject_rasterize')
+
+    def clear_keygrid(self):
+        check(lib.vs_keygrid_clear(self.ctx.handle, _ptr(self.keygrid), self.keygrid.numel(), 4,
+                                   _stream(self.device)), 'vs_keygrid_clear')
 
     def finalize(self, out=None, count_nan=False):
         """lib/proj_to_grid.py:62-79 + produce_dsm.py:58 -> float32 (n_size, e_size) per-view DSM (device)."""
@@ -143,6 +149,65 @@ class DsmEngine:
         """aggregate_2p5d.py:65-81 -> float32 (n_size, e_size) fused DSM (device)."""
         mean = self.fuse(views)
         return self.median3x3(mean, count_nan=True)
+
+    # ---- host-buffer entry point (what aggregate_2p5d.run_fuse uses) ---------------------------------------
+    def process_host(self, depths_host, mats, views_out_host=None, fused_out_host=None, stack=None, fuse=True):
+        """Depth maps in (pinned) host memory -> per-view DSMs and fused DSM back in host memory.
+
+        Three streams: H2D of view v+1, kernels of view v and D2H of DSM v-1 overlap; two device depth slots.
+        depths_host: list of float32 (H,W) CPU tensors (pinned for async copies); mats: list of 4x4 arrays.
+        views_out_host: optional (V, n_size, e_size) pinned CPU tensor; fused_out_host: optional (n_size, e_size).
+        Returns (stack (device), fused (device or None)).  Synchronises before returning."""
+        V = len(depths_host)
+        dev = self.device
+        if stack is None:
+            stack = torch.empty((V, self.n_size, self.e_size), dtype=torch.float32, device=dev)
+        if not hasattr(self, '_streams'):
+            self._streams = [torch.cuda.Stream(device=dev) for _ in range(3)]
+        s_in, s_comp, s_out = self._streams
+        cur = torch.cuda.current_stream(dev)
+        for s in self._streams:
+            s.wait_stream(cur)
+        shapes = {tuple(d.shape) for d in depths_host}
+        slots = {}
+        for shp in shapes:
+            key = ('slot', shp)
+            if key not in self.__dict__.setdefault('_slots', {}):
+                self._slots[key] = [torch.empty(shp, dtype=torch.float32, device=dev) for _ in range(2)]
+            slots[shp] = self._slots[key]
+        comp_done = [None] * V
+        for v in range(V):
+            shp = tuple(depths_host[v].shape)
+            slot = slots[shp][v % 2]
+            if v >= 2:
+                s_in.wait_event(comp_done[v - 2])
+            with torch.cuda.stream(s_in):
+                slot.copy_(depths_host[v], non_blocking=True)
+                ev_in = torch.cuda.Event()
+                ev_in.record(s_in)
+            s_comp.wait_event(ev_in)
+            with torch.cuda.stream(s_comp):
+                self.view_dsm(slot, mats[v], out=stack[v])
+                comp_done[v] = torch.cuda.Event()
+                comp_done[v].record(s_comp)
+            if views_out_host is not None:
+                s_out.wait_event(comp_done[v])
+                with torch.cuda.stream(s_out):
+                    views_out_host[v].copy_(stack[v], non_blocking=True)
+        fused = None
+        if fuse:
+            with torch.cuda.stream(s_comp):
+                fused = self.fuse_and_blur(stack)
+                ev = torch.cuda.Event()
+                ev.record(s_comp)
+            if fused_out_host is not None:
+                s_out.wait_event(ev)
+                with torch.cuda.stream(s_out):
+                    fused_out_host.copy_(fused, non_blocking=True)
+        for s in self._streams:
+            cur.wait_stream(s)
+        cur.synchronize()
+        return stack, fused
 
     def launch_count(self):
         return self.ctx.launch_count()
