@@ -20,9 +20,7 @@ Prints ONE JSON line on rank 0.
 import argparse
 import json
 import os
-import subprocess
 import sys
-import tempfile
 import time
 
 import numpy as np
@@ -45,59 +43,65 @@ def load_peaks():
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
-         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
-         'clocks_event_reasons.sw_power_cap')
+    """SM clock + throttle reasons sampled through NVML every ~5 ms during the timed region (the region is a few
+    tens of ms, too short for `nvidia-smi -lms`); same fields as the B200_PROFILING.md clocks line."""
 
     def __init__(self, index=0):
         self.index = index
-        self.proc = None
-        self.path = None
+        self.samples = []
+        self.thread = None
+        self.stop_flag = False
+        self.smax = None
+
+    def _run(self):
+        import pynvml as nv
+        R = {'hw_slowdown': nv.nvmlClocksEventReasonHwSlowdown,
+             'hw_thermal_slowdown': nv.nvmlClocksEventReasonHwThermalSlowdown,
+             'sw_thermal_slowdown': nv.nvmlClocksEventReasonSwThermalSlowdown,
+             'sw_power_cap': nv.nvmlClocksEventReasonSwPowerCap}
+        h = self.handle
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                self.samples.append((sm, pw, [k for k, bit in R.items() if mask & bit]))
+            except Exception:
+                pass
+            time.sleep(0.004)
 
     def start(self):
         try:
-            fd, self.path = tempfile.mkstemp(prefix='clocks_', suffix='.csv')
-            os.close(fd)
-            self.fp = open(self.path, 'w')
-            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
-                                         stdout=self.fp, stderr=subprocess.DEVNULL)
+            import threading
+            import pynvml as nv
+            nv.nvmlInit()
+            # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            idx = self.index
+            if vis:
+                try:
+                    idx = int(vis.split(',')[self.index])
+                except Exception:
+                    pass
+            self.handle = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.smax = nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM)
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
         except Exception:
-            self.proc = None
+            self.thread = None
 
     def stop(self):
-        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
-        if self.proc is None:
+        out = {'sm_mhz': None, 'sm_max_mhz': self.smax, 'reasons': [], 'samples': 0}
+        if self.thread is None:
             return out
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        self.fp.close()
-        sm, smax, power, reasons = [], [], [], set()
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        with open(self.path) as fp:
-            for line in fp:
-                t = [x.strip() for x in line.split(',')]
-                if len(t) < 9:
-                    continue
-                try:
-                    sm.append(float(t[1]))
-                    smax.append(float(t[2]))
-                    power.append(float(t[3]))
-                except ValueError:
-                    continue
-                for name, val in zip(names, t[5:9]):
-                    if val.lower().startswith('active'):
-                        reasons.add(name)
-        os.unlink(self.path)
-        if sm:
-            # "under load": samples in the upper half of the observed power range
-            p = np.array(power)
-            load = p >= (p.min() + 0.5 * (p.max() - p.min())) if p.max() > p.min() else np.ones(len(p), bool)
-            out = {'sm_mhz': float(np.median(np.array(sm)[load])), 'sm_max_mhz': float(max(smax)),
-                   'reasons': sorted(reasons), 'samples': len(sm), 'power_w_max': float(p.max())}
+        self.stop_flag = True
+        self.thread.join(timeout=2)
+        if self.samples:
+            sm = np.array([s[0] for s in self.samples], dtype=float)
+            reasons = sorted({r for s in self.samples for r in s[2]})
+            out = {'sm_mhz': float(np.median(sm)), 'sm_min_mhz': float(sm.min()), 'sm_max_mhz': float(self.smax),
+                   'reasons': reasons, 'samples': len(self.samples),
+                   'power_w_max': float(max(s[1] for s in self.samples))}
         return out
 
 

@@ -29,7 +29,7 @@ class vs_aoi(C.Structure):
 
 
 class vs_fit_info(C.Structure):
-    _fields_ = [('degree', C.c_int32), ('n_terms', C.c_int32),
+    _fields_ = [('degree', C.c_int32), ('n_terms', C.c_int32), ('mixed', C.c_int32), ('reserved', C.c_int32),
                 ('max_err_cells', C.c_double), ('max_err_alt_m', C.c_double),
                 ('box_center', C.c_double * 3), ('box_half', C.c_double * 3)]
 
@@ -126,7 +126,7 @@ class Context:
     def set_aoi(self, aoi_struct, max_degree=5):
         info = vs_fit_info()
         check(lib.vs_set_aoi(self.handle, C.byref(aoi_struct), int(max_degree), C.byref(info)), 'vs_set_aoi')
-        self.fit = {'degree': info.degree, 'n_terms': info.n_terms, 'max_err_cells': info.max_err_cells,
+        self.fit = {'degree': info.degree, 'n_terms': info.n_terms, 'mixed': info.mixed, 'max_err_cells': info.max_err_cells,
                     'max_err_alt_m': info.max_err_alt_m, 'box_center': list(info.box_center),
                     'box_half': list(info.box_half)}
         return self.fit

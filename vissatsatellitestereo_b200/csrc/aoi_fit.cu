@@ -115,6 +115,15 @@ double eval_poly_host(int D, const double* c, double u, double v, double w) {
     return NAN;
 }
 
+float eval_poly_host_f32(int D, const float* c, float u, float v, float w) {
+    switch (D) {
+        case 3: return vs_poly_eval<3, float>(c, u, v, w);
+        case 4: return vs_poly_eval<4, float>(c, u, v, w);
+        case 5: return vs_poly_eval<5, float>(c, u, v, w);
+    }
+    return NAN;
+}
+
 // deterministic quasi-random numbers in [-1, 1] for the held-out validation points
 double halton(int index, int base) {
     double f = 1, r = 0;
@@ -258,33 +267,57 @@ extern "C" int vs_set_aoi(vs_ctx* ctx, const vs_aoi* aoi, int max_degree, vs_fit
             B[r * 3 + 2] = (long double)vals[3 * r + 2];
         }
         if (!lstsq_qr(A, B, m, nt, 3, X)) continue;
-        VsPoly cand = P;
-        cand.degree = D;
-        cand.n_terms = nt;
-        for (int t = 0; t < nt; ++t)
-            for (int o = 0; o < 3; ++o) cand.coef[o][t] = (double)X[(size_t)t * 3 + o];
-        double err_cells = 0, err_alt = 0, err_m = 0;
-        for (int i = 0; i < n_test; ++i) {
-            double u = test_uvw[3 * i], v = test_uvw[3 * i + 1], w = test_uvw[3 * i + 2];
-            double colf = (test_out[3 * i] - aoi->ul_e) / aoi->col_res;
-            double rowf = (aoi->ul_n - test_out[3 * i + 1]) / aoi->row_res;
-            double dc = fabs(eval_poly_host(D, cand.coef[0], u, v, w) - colf);
-            double dr = fabs(eval_poly_host(D, cand.coef[1], u, v, w) - rowf);
-            double da = fabs(eval_poly_host(D, cand.coef[2], u, v, w) - test_out[3 * i + 2]);
-            err_cells = fmax(err_cells, fmax(dc, dr));
-            err_m = fmax(err_m, fmax(dc * aoi->col_res, dr * aoi->row_res));
-            err_alt = fmax(err_alt, da);
+        bool accepted = false;
+        for (int mixed = 1; mixed >= 0 && !accepted; --mixed) {
+            VsPoly cand = P;
+            cand.degree = D;
+            cand.n_terms = nt;
+            cand.mixed = mixed;
+            for (int t = 0; t < nt; ++t)
+                for (int o = 0; o < 3; ++o) cand.coef[o][t] = (double)X[(size_t)t * 3 + o];
+            for (int i = 0; i <= D; ++i)
+                for (int j = 0; j <= D - i; ++j)
+                    for (int k = 0; k <= D - i - j; ++k)
+                        for (int o = 0; o < 3; ++o) {
+                            const double cf = cand.coef[o][vs_poly_index(D, i, j, k)];
+                            if (i + j + k <= 2) {
+                                cand.coef2[o][vs_poly_index(2, i, j, k)] = cf;
+                                cand.coefR[o][vs_poly_index(D, i, j, k)] = 0.0f;
+                            } else {
+                                cand.coefR[o][vs_poly_index(D, i, j, k)] = (float)cf;
+                            }
+                        }
+            double err_cells = 0, err_alt = 0, err_m = 0;
+            for (int i = 0; i < n_test; ++i) {
+                const double u = test_uvw[3 * i], v = test_uvw[3 * i + 1], w = test_uvw[3 * i + 2];
+                const double want[3] = {(test_out[3 * i] - aoi->ul_e) / aoi->col_res,
+                                        (aoi->ul_n - test_out[3 * i + 1]) / aoi->row_res, test_out[3 * i + 2]};
+                double got[3];
+                for (int o = 0; o < 3; ++o) {
+                    if (mixed)  // exactly what the device evaluates
+                        got[o] = vs_poly_eval<2>(cand.coef2[o], u, v, w) +
+                                 (double)eval_poly_host_f32(D, cand.coefR[o], (float)u, (float)v, (float)w);
+                    else
+                        got[o] = eval_poly_host(D, cand.coef[o], u, v, w);
+                }
+                const double dc = fabs(got[0] - want[0]), dr = fabs(got[1] - want[1]), da = fabs(got[2] - want[2]);
+                err_cells = fmax(err_cells, fmax(dc, dr));
+                err_m = fmax(err_m, fmax(dc * aoi->col_res, dr * aoi->row_res));
+                err_alt = fmax(err_alt, da);
+            }
+            const bool ok = err_m <= tol_m && err_alt <= tol_m;
+            if (ok || (D == max_degree && mixed == 0)) {
+                // keep the last attempt's errors for diagnostics; only a validated fit is activated
+                ctx->fit.degree = ok ? D : 0;
+                ctx->fit.n_terms = ok ? nt : 0;
+                ctx->fit.mixed = ok ? mixed : 0;
+                ctx->fit.max_err_cells = err_cells;
+                ctx->fit.max_err_alt_m = err_alt;
+                if (ok) P = cand;
+                accepted = true;
+            }
         }
-        bool ok = err_m <= tol_m && err_alt <= tol_m;
-        if (ok || D == max_degree) {
-            // keep the best effort for diagnostics; only a validated fit is activated
-            ctx->fit.degree = ok ? D : 0;
-            ctx->fit.n_terms = ok ? nt : 0;
-            ctx->fit.max_err_cells = err_cells;
-            ctx->fit.max_err_alt_m = err_alt;
-            if (ok) P = cand;
-            break;
-        }
+        if (accepted) break;
     }
     if (info) *info = ctx->fit;
     return VS_OK;

@@ -17,21 +17,55 @@ __host__ __device__ constexpr int vs_poly_index(int D, int i, int j, int k) {
 __host__ __device__ constexpr int vs_poly_terms(int D) { return (D + 1) * (D + 2) * (D + 3) / 6; }
 
 // Nested Horner: sum_i u^i ( sum_j v^j ( sum_k w^k c_ijk ) ), n_terms - 1 fused multiply-adds.
-template <int D>
-__host__ __device__ __forceinline__ double vs_poly_eval(const double* __restrict__ c, double u, double v, double w) {
-    double r = 0.0;
+__host__ __device__ __forceinline__ double vs_fma_t(double a, double b, double c) { return fma(a, b, c); }
+__host__ __device__ __forceinline__ float vs_fma_t(float a, float b, float c) { return fmaf(a, b, c); }
+
+template <int D, typename T = double>
+__host__ __device__ __forceinline__ T vs_poly_eval(const T* __restrict__ c, T u, T v, T w) {
+    T r = 0;
 #pragma unroll
     for (int i = D; i >= 0; --i) {
-        double a = 0.0;
+        T a = 0;
 #pragma unroll
         for (int j = D - i; j >= 0; --j) {
             const int kmax = D - i - j;
-            double b = c[vs_poly_index(D, i, j, kmax)];
+            T b = c[vs_poly_index(D, i, j, kmax)];
 #pragma unroll
-            for (int k = kmax - 1; k >= 0; --k) b = fma(b, w, c[vs_poly_index(D, i, j, k)]);
-            a = (j == D - i) ? b : fma(a, v, b);
+            for (int k = kmax - 1; k >= 0; --k) b = vs_fma_t(b, w, c[vs_poly_index(D, i, j, k)]);
+            a = (j == D - i) ? b : vs_fma_t(a, v, b);
         }
-        r = (i == D) ? a : fma(r, u, a);
+        r = (i == D) ? a : vs_fma_t(r, u, a);
     }
     return r;
+}
+
+// The same evaluation for L points in lockstep (terms outer, points inner): every coefficient is fetched once
+// and used L times, which matters on sm_100a where a DFMA cannot take a constant-bank operand.
+// Bit-identical to L calls of vs_poly_eval.
+template <int D, int L, typename T>
+__device__ __forceinline__ void vs_poly_eval_n(const T* __restrict__ c, const T (&u)[L], const T (&v)[L], const T (&w)[L],
+                                               T (&out)[L]) {
+    T r[L], a[L], b[L];
+#pragma unroll
+    for (int i = D; i >= 0; --i) {
+#pragma unroll
+        for (int j = D - i; j >= 0; --j) {
+            const int kmax = D - i - j;
+            const T ck = c[vs_poly_index(D, i, j, kmax)];
+#pragma unroll
+            for (int p = 0; p < L; ++p) b[p] = ck;
+#pragma unroll
+            for (int k = kmax - 1; k >= 0; --k) {
+                const T cc = c[vs_poly_index(D, i, j, k)];
+#pragma unroll
+                for (int p = 0; p < L; ++p) b[p] = vs_fma_t(b[p], w[p], cc);
+            }
+#pragma unroll
+            for (int p = 0; p < L; ++p) a[p] = (j == D - i) ? b[p] : vs_fma_t(a[p], v[p], b[p]);
+        }
+#pragma unroll
+        for (int p = 0; p < L; ++p) r[p] = (i == D) ? a[p] : vs_fma_t(r[p], u[p], a[p]);
+    }
+#pragma unroll
+    for (int p = 0; p < L; ++p) out[p] = r[p];
 }

@@ -31,24 +31,12 @@ struct RasterParams {
     int degree;
 };
 
-struct PolyCoefs {
-    double c[3][VS_MAX_TERMS];
-};
-
 __device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
     float4 r;
     asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
                  : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
                  : "l"(p));
     return r;
-}
-
-template <int D>
-__device__ __forceinline__ void eval3(const PolyCoefs& pc, double u, double v, double w, double& colf, double& rowf,
-                                      double& alt) {
-    colf = vs_poly_eval<D>(pc.c[0], u, v, w);
-    rowf = vs_poly_eval<D>(pc.c[1], u, v, w);
-    alt = vs_poly_eval<D>(pc.c[2], u, v, w);
 }
 
 // block-level reduction of the per-thread counters, one atomic per counter per block
@@ -88,92 +76,171 @@ __device__ __noinline__ int scatter_exact_point(const VsExactParams* __restrict_
     return 0;
 }
 
-template <int D>
-__global__ void __launch_bounds__(kThreads, 3)
+// Coefficients of the per-AOI polynomial as the kernel consumes them (kernel parameter, constant bank).
+struct PolyCoefs {
+    double c64[3][VS_MAX_TERMS];  // MIXED: degree-2 part (10 terms, degree-2 index order); else all terms
+    float c32[3][VS_MAX_TERMS];   // MIXED: terms of degree 3..D (degree-D index order, low terms zero)
+};
+
+constexpr int PX = 4;  // pixels per thread per step (one 16-byte load), evaluated in lockstep
+
+template <int D, bool MIXED>
+__global__ void __launch_bounds__(kThreads, 2)
 k_unproject_scatter(RasterParams p, PolyCoefs pc, const VsExactParams* __restrict__ ex, const float* __restrict__ depth,
                     uint32_t* __restrict__ keygrid, float* __restrict__ height_map,
                     unsigned long long* __restrict__ stats) {
     const int64_t n_pix = (int64_t)p.H * p.W;
-    const int64_t n_chunks = (n_pix + 3) >> 2;
+    const int64_t n_chunks = (n_pix + PX - 1) / PX;
+    const bool audit = stats != nullptr;
     unsigned n_valid = 0, n_ingrid = 0, n_amb = 0, n_exact = 0;
 
     for (int64_t chunk = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; chunk < n_chunks;
          chunk += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t base = chunk << 2;
-        float d4[4];
-        if (base + 3 < n_pix) {
-            float4 t = ld_stream_f4(reinterpret_cast<const float4*>(depth + base));
+        const int64_t base = chunk * PX;
+        float d4[PX];
+        if (base + PX - 1 < n_pix) {
+            const float4 t = ld_stream_f4(reinterpret_cast<const float4*>(depth + base));
             d4[0] = t.x; d4[1] = t.y; d4[2] = t.z; d4[3] = t.w;
         } else {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) d4[i] = (base + i < n_pix) ? depth[base + i] : -1.0f;
+            for (int i = 0; i < PX; ++i) d4[i] = (base + i < n_pix) ? depth[base + i] : -1.0f;
         }
-        int row = (int)(base / p.W);
-        int col = (int)(base - (int64_t)row * p.W);
-        float hm[4];
-        int pend_cell = -1;      // register-level merge of same-cell neighbours
-        uint32_t pend_key = 0;
+        // aggregate_2p5d_util.py:76: depth <= 0 (and NaN) is invalid
+        bool ok[PX];
+        bool any_ok = false;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            hm[i] = CUDART_NAN_F;
-            const float df = d4[i];
-            if (df > 0.0f && base + i < n_pix) {  // aggregate_2p5d_util.py:76 (NaN fails the test as well)
-                const double d = (double)df;
-                const double fc = (double)col, fr = (double)row;
-                // aggregate_2p5d_util.py:86-90: M . [col, row, 1, depth], then divide by w
-                const double hw = fma(p.M3[0], fc, fma(p.M3[1], fr, fma(p.M3[3], d, p.M3[2])));
-                const double rw = 1.0 / hw;
-                const double u = fma(p.Mn[0][0], fc, fma(p.Mn[0][1], fr, fma(p.Mn[0][3], d, p.Mn[0][2]))) * rw;
-                const double v = fma(p.Mn[1][0], fc, fma(p.Mn[1][1], fr, fma(p.Mn[1][3], d, p.Mn[1][2]))) * rw;
-                const double w = fma(p.Mn[2][0], fc, fma(p.Mn[2][1], fr, fma(p.Mn[2][3], d, p.Mn[2][2]))) * rw;
-                // finite position <=> valid point (aggregate_2p5d_util.py:92); non-finite ones can never pass
-                // the bounds mask of lib/proj_to_grid.py:48
-                if (fabs(u) < CUDART_INF && fabs(v) < CUDART_INF && fabs(w) < CUDART_INF) {
-                    ++n_valid;
-                    hm[i] = (float)fma(w, p.half_z, p.center_z);
-                    if (fabs(u) <= 1.0 && fabs(v) <= 1.0) {  // outside the box => outside the grid
-                        if (fabs(w) <= 1.0) {
-                            double colf, rowf, alt;
-                            eval3<D>(pc, u, v, w, colf, rowf, alt);
-                            const double cfl = floor(colf), rfl = floor(rowf);  // lib/proj_to_grid.py:42-43
-                            if (cfl >= 0.0 && rfl >= 0.0 && cfl < (double)p.xsize && rfl < (double)p.ysize) {
-                                ++n_ingrid;
-                                const double fcx = colf - cfl, frx = rowf - rfl;
-                                if (fcx < p.eps || fcx > 1.0 - p.eps || frx < p.eps || frx > 1.0 - p.eps) ++n_amb;
-                                const int cell = (int)rfl * p.xsize + (int)cfl;
-                                const uint32_t key = vs_key32((float)alt);
-                                if (cell == pend_cell) {
-                                    pend_key = max(pend_key, key);
-                                } else {
-                                    if (pend_cell >= 0) atomicMax(keygrid + pend_cell, pend_key);
-                                    pend_cell = cell;
-                                    pend_key = key;
-                                }
-                            }
-                        } else {
-                            ++n_exact;
-                            const int r = scatter_exact_point(ex, u, v, w, keygrid);
-                            n_ingrid += (r != 0);
-                            n_amb += (r == 2);
-                        }
-                    }
-                }
+        for (int i = 0; i < PX; ++i) {
+            ok[i] = d4[i] > 0.0f;
+            any_ok |= ok[i];
+        }
+        if (!any_ok) {
+            if (height_map != nullptr) {
+#pragma unroll
+                for (int i = 0; i < PX; ++i)
+                    if (base + i < n_pix) height_map[base + i] = CUDART_NAN_F;
             }
-            if (++col == p.W) {
-                col = 0;
-                ++row;
+            continue;
+        }
+        const int row0 = (int)(base / p.W);
+        const int col0 = (int)(base - (int64_t)row0 * p.W);
+
+        // ---- aggregate_2p5d_util.py:86-90: X = M . [col, row, 1, depth]; (u, v, w) = box-normalised X/X_3
+        double u[PX], v[PX], w[PX];
+        {
+            const bool one_row = col0 + PX <= p.W;
+            const double fr0 = (double)row0;
+            double rt[4];  // M[k][1]*row + M[k][2], shared by the pixels of one image row
+            rt[0] = fma(p.Mn[0][1], fr0, p.Mn[0][2]);
+            rt[1] = fma(p.Mn[1][1], fr0, p.Mn[1][2]);
+            rt[2] = fma(p.Mn[2][1], fr0, p.Mn[2][2]);
+            rt[3] = fma(p.M3[1], fr0, p.M3[2]);
+#pragma unroll
+            for (int i = 0; i < PX; ++i) {
+                double r0 = rt[0], r1 = rt[1], r2 = rt[2], r3 = rt[3];
+                int col = col0 + i;
+                if (!one_row && col >= p.W) {  // chunk straddles image rows (W not a multiple of 4)
+                    const int64_t idx = base + i;
+                    const int row = (int)(idx / p.W);
+                    col = (int)(idx - (int64_t)row * p.W);
+                    const double fr = (double)row;
+                    r0 = fma(p.Mn[0][1], fr, p.Mn[0][2]);
+                    r1 = fma(p.Mn[1][1], fr, p.Mn[1][2]);
+                    r2 = fma(p.Mn[2][1], fr, p.Mn[2][2]);
+                    r3 = fma(p.M3[1], fr, p.M3[2]);
+                }
+                const double fc = (double)col, d = (double)d4[i];
+                const double hw = fma(p.M3[0], fc, fma(p.M3[3], d, r3));
+                const double rw = 1.0 / hw;
+                u[i] = fma(p.Mn[0][0], fc, fma(p.Mn[0][3], d, r0)) * rw;
+                v[i] = fma(p.Mn[1][0], fc, fma(p.Mn[1][3], d, r1)) * rw;
+                w[i] = fma(p.Mn[2][0], fc, fma(p.Mn[2][3], d, r2)) * rw;
             }
         }
-        if (pend_cell >= 0) atomicMax(keygrid + pend_cell, pend_key);
+        // ---- classification on float32 copies (the box has a margin, so float32 rounding at its faces is
+        // harmless; a non-finite position fails every test, aggregate_2p5d_util.py:92 / proj_to_grid.py:48)
+        float uf[PX], vf[PX], wf[PX];
+        bool in_box[PX], in_alt[PX];
+        float hm[PX];
+#pragma unroll
+        for (int i = 0; i < PX; ++i) {
+            uf[i] = (float)u[i];
+            vf[i] = (float)v[i];
+            wf[i] = (float)w[i];
+            const bool finite = fabsf(uf[i]) < CUDART_INF_F && fabsf(vf[i]) < CUDART_INF_F && fabsf(wf[i]) < CUDART_INF_F;
+            ok[i] = ok[i] && finite;
+            in_box[i] = ok[i] && fabsf(uf[i]) <= 1.0f && fabsf(vf[i]) <= 1.0f;  // outside the box => outside the grid
+            in_alt[i] = fabsf(wf[i]) <= 1.0f;
+            n_valid += ok[i];
+            hm[i] = ok[i] ? (float)fma(w[i], p.half_z, p.center_z) : CUDART_NAN_F;
+        }
         if (height_map != nullptr) {
-            if (base + 3 < n_pix) {
+            if (base + PX - 1 < n_pix) {
                 *reinterpret_cast<float4*>(height_map + base) = make_float4(hm[0], hm[1], hm[2], hm[3]);
             } else {
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
+                for (int i = 0; i < PX; ++i)
                     if (base + i < n_pix) height_map[base + i] = hm[i];
             }
         }
+
+        // ---- ENU -> (fractional col, fractional row, altitude): the per-AOI polynomial, 4 pixels in lockstep
+        int ci[PX], ri[PX];
+        bool amb[PX];
+        uint32_t key[PX];
+#pragma unroll
+        for (int o = 0; o < 3; ++o) {
+            double val[PX];
+            if (MIXED) {
+                vs_poly_eval_n<2, PX, double>(pc.c64[o], u, v, w, val);
+                float hi[PX];
+                vs_poly_eval_n<D, PX, float>(pc.c32[o], uf, vf, wf, hi);
+#pragma unroll
+                for (int i = 0; i < PX; ++i) val[i] += (double)hi[i];
+            } else {
+                vs_poly_eval_n<D, PX, double>(pc.c64[o], u, v, w, val);
+            }
+#pragma unroll
+            for (int i = 0; i < PX; ++i) {
+                if (o == 2) {
+                    key[i] = vs_key32((float)val[i]);
+                } else {
+                    const int q = __double2int_rd(val[i]);  // floor, lib/proj_to_grid.py:42-43
+                    if (o == 0) ci[i] = q; else ri[i] = q;
+                    if (audit) {
+                        const bool a = fabs(val[i] - rint(val[i])) < p.eps;
+                        amb[i] = (o == 0) ? a : (amb[i] || a);
+                    }
+                }
+            }
+        }
+
+        // ---- lib/proj_to_grid.py:44-61: bounds mask + per-cell max; same-cell neighbours merge in registers
+        int pend_cell = -1;
+        uint32_t pend_key = 0;
+#pragma unroll
+        for (int i = 0; i < PX; ++i) {
+            if (!in_box[i]) continue;
+            if (in_alt[i]) {
+                if ((unsigned)ci[i] < (unsigned)p.xsize && (unsigned)ri[i] < (unsigned)p.ysize) {
+                    ++n_ingrid;
+                    if (audit) n_amb += amb[i];
+                    const int cell = ri[i] * p.xsize + ci[i];
+                    if (cell == pend_cell) {
+                        pend_key = max(pend_key, key[i]);
+                    } else {
+                        if (pend_cell >= 0) atomicMax(keygrid + pend_cell, pend_key);
+                        pend_cell = cell;
+                        pend_key = key[i];
+                    }
+                }
+            } else {  // outside the fitted altitude range: exact chain, out of line (rare)
+                ++n_exact;
+                const int r = scatter_exact_point(ex, u[i], v[i], w[i], keygrid);
+                n_ingrid += (r != 0);
+                n_amb += (r == 2);
+            }
+        }
+        if (pend_cell >= 0) atomicMax(keygrid + pend_cell, pend_key);
     }
     flush_stats(stats, n_valid, n_ingrid, n_amb, n_exact);
 }
@@ -292,15 +359,29 @@ int vs_unproject_rasterize(vs_ctx* ctx, const float* depth, int32_t H, int32_t W
     VsEllipsoidConsts c = vs_make_ellipsoid_consts();
     if (P.degree > 0) {
         PolyCoefs pc;
-        memcpy(pc.c, P.coef, sizeof(pc.c));
+        memset(&pc, 0, sizeof(pc));
+        if (P.mixed) {
+            for (int o = 0; o < 3; ++o) {
+                memcpy(pc.c64[o], P.coef2[o], sizeof(P.coef2[o]));
+                memcpy(pc.c32[o], P.coefR[o], sizeof(P.coefR[o]));
+            }
+        } else {
+            memcpy(pc.c64, P.coef, sizeof(pc.c64));
+        }
         const VsExactParams* ex = reinterpret_cast<const VsExactParams*>(ctx->d_exact);
-        const int grid = persistent_grid(ctx, (n_pix + 3) / 4, 8);
-        switch (P.degree) {
-            case 3: k_unproject_scatter<3><<<grid, kThreads, 0, stream>>>(p, pc, ex, depth, keygrid, height_map, d_stats); break;
-            case 4: k_unproject_scatter<4><<<grid, kThreads, 0, stream>>>(p, pc, ex, depth, keygrid, height_map, d_stats); break;
-            case 5: k_unproject_scatter<5><<<grid, kThreads, 0, stream>>>(p, pc, ex, depth, keygrid, height_map, d_stats); break;
+        const int grid = persistent_grid(ctx, (n_pix + PX - 1) / PX, 8);
+#define VS_LAUNCH_K1(DEG, MIX) \
+    k_unproject_scatter<DEG, MIX><<<grid, kThreads, 0, stream>>>(p, pc, ex, depth, keygrid, height_map, d_stats)
+        switch (P.degree * 2 + (P.mixed ? 1 : 0)) {
+            case 6: VS_LAUNCH_K1(3, false); break;
+            case 7: VS_LAUNCH_K1(3, true); break;
+            case 8: VS_LAUNCH_K1(4, false); break;
+            case 9: VS_LAUNCH_K1(4, true); break;
+            case 10: VS_LAUNCH_K1(5, false); break;
+            case 11: VS_LAUNCH_K1(5, true); break;
             default: vs_set_error("vs_unproject_rasterize: bad polynomial degree"); return VS_ERR_STATE;
         }
+#undef VS_LAUNCH_K1
         VS_CHECK_LAUNCH(ctx, "k_unproject_scatter");
     } else {
         const int grid = persistent_grid(ctx, n_pix, 4);
