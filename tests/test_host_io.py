@@ -1,0 +1,112 @@
+"""Host-side pieces of the drop-in that need no GPU: GeoTIFF and PLY I/O, view/row-band partitioning, and the
+world_size-2 row-band exchange on the gloo backend."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+
+def test_geotiff_round_trip(tmp_path):
+    from vissatsatellitestereo_b200.lib import dsm_util
+    rng = np.random.default_rng(0)
+    for shape in [(1, 1), (37, 53), (600, 700)]:
+        img = rng.normal(30, 10, size=shape).astype(np.float32)
+        img[rng.random(shape) < 0.2] = np.nan
+        f = str(tmp_path / 'a_{}_{}.tif'.format(*shape))
+        dsm_util.write_dsm_tif(img, f, (354052.3651180889, 6182702.10540914, 0.3, 0.3), (21, 'S'), nodata_val=-10000)
+        got, meta = dsm_util.read_dsm_tif(f)
+        assert got.dtype == np.float32 and np.array_equal(got, img, equal_nan=True)
+        assert meta['geo'] == (354052.3651180889, 0.3, 0.0, 6182702.10540914, 0.0, -0.3)       # lib/dsm_util.py:150
+        assert meta['zone_number'] == 21 and meta['hemisphere'] == 'S' and meta['nodata'] == -10000.0
+        assert meta['img_width'] == shape[1] and meta['img_height'] == shape[0]
+        assert meta['meta'] == {'AREA_OR_POINT': 'Area'}                                      # :157
+        assert meta['lr_easting'] == meta['ul_easting'] + (shape[1] - 1) * 0.3
+        assert dsm_util.parse_proj_str(meta['proj']) == (21, 'S')
+        if not np.isnan(img).all():
+            assert meta['alt_min'] == float(np.nanmin(img))
+    # values within np.isclose of the nodata value come back as NaN, like the reference (:69-72)
+    img = np.array([[1.0, -10000.05, -9999.0]], dtype=np.float32)
+    f = str(tmp_path / 'b.tif')
+    dsm_util.write_dsm_tif(img, f, (0.0, 0.0, 0.5, 0.5), (32, 'N'), nodata_val=-10000)
+    got, meta = dsm_util.read_dsm_tif(f)
+    assert np.isnan(got[0, 1]) and got[0, 2] == -9999.0 and meta['hemisphere'] == 'N' and meta['zone_number'] == 32
+    # libtiff (through OpenCV) reads the raster too
+    import cv2
+    assert np.array_equal(cv2.imread(f, cv2.IMREAD_UNCHANGED), img)
+    assert dsm_util.get_driver('x.tif') is not None and dsm_util.get_driver('x.xyz') is None
+
+
+def test_ply_round_trip(tmp_path):
+    from vissatsatellitestereo_b200.lib.ply_np_converter import np2ply, ply2np
+    rng = np.random.default_rng(1)
+    v = rng.normal(size=(100, 3)) * 1e5
+    c = (rng.random((100, 3)) * 255).astype(np.uint8)
+    f = str(tmp_path / 'p.ply')
+    np2ply(v, f, color=c, comments=['projection: UTM 21S'], use_double=True)     # aggregate_2p5d.py:110-113
+    d, col, com = ply2np(f)
+    assert np.array_equal(d, v) and np.array_equal(col, c) and com == ['projection: UTM 21S']
+    np2ply(v, f, use_double=False)
+    d, col, com = ply2np(f)
+    assert np.array_equal(d, v.astype(np.float32)) and col is None and com is None
+    np2ply(v[:5], f, color=c[:5], text=True)
+    d, col, _ = ply2np(f)
+    assert np.allclose(d, v[:5], atol=1e-4) and np.array_equal(col, c[:5])
+
+
+def test_partitions():
+    from vissatsatellitestereo_b200 import distributed as D
+    from vissatsatellitestereo_b200.aggregate_2p5d_util import split_big_list
+    assert D.split_views(50, 8) == [(0, 7), (7, 14), (14, 20), (20, 26), (26, 32), (32, 38), (38, 44), (44, 50)]
+    assert D.split_views(3, 4) == [(0, 1), (1, 2), (2, 3), (0, 0)]
+    bands = D.row_bands(2048, 8)
+    assert bands[0] == (0, 256) and bands[-1] == (1792, 2048)
+    assert D.band_with_halo((0, 256), 2048) == (0, 257) and D.band_with_halo((256, 512), 2048) == (255, 513)
+    assert D.band_with_halo((1792, 2048), 2048) == (1791, 2048)
+    # aggregate_2p5d_util.py:109-122
+    assert split_big_list(list(range(10)), 3) == [[0, 1, 2, 3], [4, 5, 6], [7, 8, 9]]
+    assert split_big_list([1, 2], 4) == [[1], [2]]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _exchange_worker(rank, world, port, n_rows, W, counts, out):
+    import torch.distributed as dist
+    from vissatsatellitestereo_b200 import distributed as D
+    dist.init_process_group('gloo', init_method='tcp://127.0.0.1:{}'.format(port), rank=rank, world_size=world)
+    try:
+        first = sum(counts[:rank])
+        # plane v of the global stack holds v*1e6 + row*1e3 + col
+        rows = torch.arange(n_rows, dtype=torch.float32)[:, None] * 1e3 + torch.arange(W, dtype=torch.float32)[None, :]
+        local = torch.stack([rows + (first + i) * 1e6 for i in range(counts[rank])]) if counts[rank] else \
+            torch.empty((0, n_rows, W))
+        band_stack, (r0, r1), (h0, h1) = D.exchange_rowbands(local, counts, n_rows)
+        want = torch.stack([rows[h0:h1] + v * 1e6 for v in range(sum(counts))])
+        ok = torch.equal(band_stack, want)
+        # a fake "fusion" (mean over views of the band) and the gather of the bands on rank 0
+        band = band_stack.mean(dim=0)[r0 - h0: r1 - h0].contiguous()
+        full = D.gather_bands(band, n_rows, W)
+        if rank == 0:
+            ok = ok and torch.allclose(full, rows + (sum(counts) - 1) / 2 * 1e6)
+        out[rank] = bool(ok) and (r0, r1) == D.row_bands(n_rows, world)[rank]
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('n_rows,counts', [(37, [3, 2]), (8, [1, 4]), (5, [2, 0])])
+def test_rowband_exchange_world2_gloo(n_rows, counts):
+    """the all-to-all that turns view-sharded per-view DSMs into row-band-sharded stacks."""
+    import torch.multiprocessing as mp
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_exchange_worker, args=(world, port, n_rows, 11, counts, out), nprocs=world, join=True)
+    assert dict(out) == {0: True, 1: True}

@@ -43,10 +43,12 @@ VS_DEF_SORTNET(64)
 // (s[(k-1)/2] + s[k/2]) / 2 with static register indexing
 template <int N>
 __device__ __forceinline__ float middle_of_sorted(const float (&s)[N], int k) {
+    // k <= N, so both middle positions are <= N/2: only the lower half of the sorted array is ever read and
+    // the compiler drops every compare-exchange that feeds the upper half only.
     const int ilo = (k - 1) >> 1, ihi = k >> 1;
     float lo = s[0], hi = s[0];
 #pragma unroll
-    for (int i = 1; i < N; ++i) {
+    for (int i = 1; i <= N / 2; ++i) {
         lo = (i == ilo) ? s[i] : lo;
         hi = (i == ihi) ? s[i] : hi;
     }
