@@ -64,7 +64,8 @@ typedef struct vs_aoi {
 typedef struct vs_fit_info {
     int32_t degree;          /* 3..5, or 0 = exact chain for every point */
     int32_t n_terms;
-    int32_t mixed;           /* 1: terms of degree >= 3 are evaluated in float32 (validated like the rest) */
+    int32_t mixed;           /* 0: all terms in float64; 1 or 2: only terms of total degree <= this are float64,
+                                higher terms are evaluated in float32 (validated like the rest) */
     int32_t reserved;
     double max_err_cells;    /* max |poly - exact| of the fractional row/col on held-out points */
     double max_err_alt_m;    /* max |poly - exact| altitude (m) on held-out points */

@@ -268,25 +268,29 @@ extern "C" int vs_set_aoi(vs_ctx* ctx, const vs_aoi* aoi, int max_degree, vs_fit
         }
         if (!lstsq_qr(A, B, m, nt, 3, X)) continue;
         bool accepted = false;
-        for (int mixed = 1; mixed >= 0 && !accepted; --mixed) {
+        // cheapest evaluation first: float64 only for the terms of degree <= d64, float32 above; 0 = all float64
+        const int d64_order[3] = {1, 2, 0};
+        for (int q = 0; q < 3 && !accepted; ++q) {
+            const int d64 = d64_order[q];
             VsPoly cand = P;
             cand.degree = D;
             cand.n_terms = nt;
-            cand.mixed = mixed;
+            cand.d64 = d64;
             for (int t = 0; t < nt; ++t)
                 for (int o = 0; o < 3; ++o) cand.coef[o][t] = (double)X[(size_t)t * 3 + o];
-            for (int i = 0; i <= D; ++i)
-                for (int j = 0; j <= D - i; ++j)
-                    for (int k = 0; k <= D - i - j; ++k)
-                        for (int o = 0; o < 3; ++o) {
-                            const double cf = cand.coef[o][vs_poly_index(D, i, j, k)];
-                            if (i + j + k <= 2) {
-                                cand.coef2[o][vs_poly_index(2, i, j, k)] = cf;
-                                cand.coefR[o][vs_poly_index(D, i, j, k)] = 0.0f;
-                            } else {
-                                cand.coefR[o][vs_poly_index(D, i, j, k)] = (float)cf;
+            if (d64 > 0)
+                for (int i = 0; i <= D; ++i)
+                    for (int j = 0; j <= D - i; ++j)
+                        for (int k = 0; k <= D - i - j; ++k)
+                            for (int o = 0; o < 3; ++o) {
+                                const double cf = cand.coef[o][vs_poly_index(D, i, j, k)];
+                                if (i + j + k <= d64) {
+                                    cand.coefLo[o][vs_poly_index(d64, i, j, k)] = cf;
+                                    cand.coefR[o][vs_poly_index(D, i, j, k)] = 0.0f;
+                                } else {
+                                    cand.coefR[o][vs_poly_index(D, i, j, k)] = (float)cf;
+                                }
                             }
-                        }
             double err_cells = 0, err_alt = 0, err_m = 0;
             for (int i = 0; i < n_test; ++i) {
                 const double u = test_uvw[3 * i], v = test_uvw[3 * i + 1], w = test_uvw[3 * i + 2];
@@ -294,11 +298,11 @@ extern "C" int vs_set_aoi(vs_ctx* ctx, const vs_aoi* aoi, int max_degree, vs_fit
                                         (aoi->ul_n - test_out[3 * i + 1]) / aoi->row_res, test_out[3 * i + 2]};
                 double got[3];
                 for (int o = 0; o < 3; ++o) {
-                    if (mixed)  // exactly what the device evaluates
-                        got[o] = vs_poly_eval<2>(cand.coef2[o], u, v, w) +
-                                 (double)eval_poly_host_f32(D, cand.coefR[o], (float)u, (float)v, (float)w);
-                    else
-                        got[o] = eval_poly_host(D, cand.coef[o], u, v, w);
+                    // exactly what the device evaluates
+                    const double hi = d64 ? (double)eval_poly_host_f32(D, cand.coefR[o], (float)u, (float)v, (float)w) : 0.0;
+                    if (d64 == 1) got[o] = vs_poly_eval<1>(cand.coefLo[o], u, v, w) + hi;
+                    else if (d64 == 2) got[o] = vs_poly_eval<2>(cand.coefLo[o], u, v, w) + hi;
+                    else got[o] = eval_poly_host(D, cand.coef[o], u, v, w);
                 }
                 const double dc = fabs(got[0] - want[0]), dr = fabs(got[1] - want[1]), da = fabs(got[2] - want[2]);
                 err_cells = fmax(err_cells, fmax(dc, dr));
@@ -306,11 +310,11 @@ extern "C" int vs_set_aoi(vs_ctx* ctx, const vs_aoi* aoi, int max_degree, vs_fit
                 err_alt = fmax(err_alt, da);
             }
             const bool ok = err_m <= tol_m && err_alt <= tol_m;
-            if (ok || (D == max_degree && mixed == 0)) {
+            if (ok || (D == max_degree && d64 == 0)) {
                 // keep the last attempt's errors for diagnostics; only a validated fit is activated
                 ctx->fit.degree = ok ? D : 0;
                 ctx->fit.n_terms = ok ? nt : 0;
-                ctx->fit.mixed = ok ? mixed : 0;
+                ctx->fit.mixed = ok ? d64 : 0;
                 ctx->fit.max_err_cells = err_cells;
                 ctx->fit.max_err_alt_m = err_alt;
                 if (ok) P = cand;

@@ -134,11 +134,13 @@ __global__ void __launch_bounds__(kThreads)
 k_grid_finalize(const Key* __restrict__ keygrid, int W, int H, typename KeyTraits<Key>::value_t* __restrict__ filled_out,
                 float* __restrict__ blur_out, int simd_cols, unsigned long long* __restrict__ nan_count) {
     typedef typename KeyTraits<Key>::value_t T;
-    __shared__ T s_raw[TR * TS];          // decoded keys, PRE-fill (the hole fill must not cascade, :65)
-    __shared__ float s_fill[TR * TS];     // float32 tile after the fill (what cv2.medianBlur sees)
+    constexpr bool kSameTile = sizeof(T) == sizeof(float);   // float32 keys: one tile serves fill and blur
+    __shared__ T s_raw[TR * TS];                    // decoded keys; holes are patched in place after phase 2
+    __shared__ float s_fill32[kSameTile ? 1 : TR * TS];   // float32 copy (what cv2.medianBlur sees) for the f64 path
     __shared__ unsigned short s_hole_pos[(TILE + 2) * (TILE + 2)];
     __shared__ T s_hole_val[(TILE + 2) * (TILE + 2)];
     __shared__ int s_nholes, s_has_nan;
+    float* s_fill = kSameTile ? reinterpret_cast<float*>(s_raw) : s_fill32;
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int tid = ty * 32 + tx;
     const int tx0 = blockIdx.x * TILE, ty0 = blockIdx.y * TILE;
@@ -148,42 +150,25 @@ k_grid_finalize(const Key* __restrict__ keygrid, int W, int H, typename KeyTrait
     }
     __syncthreads();
 
-    // 1. decode keys (+2 halo); outside the grid -> NaN (the fill only uses in-range neighbours, :73);
-    //    list the holes = NaN cells inside the grid within the 1-cell halo
-#pragma unroll
-    for (int it = 0; it < (TR + 7) / 8; ++it) {
-        const int r = ty + 8 * it;
-        if (r < TR) {  // warp-uniform
-            const int gy = ty0 - 2 + r;
-            const bool row_ok = gy >= 0 && gy < H;
-            const Key* __restrict__ row = keygrid + (size_t)(row_ok ? gy : 0) * W;
-            const bool row_inner = r >= 1 && r <= TILE + 2;
-#pragma unroll
-            for (int pass = 0; pass < 2; ++pass) {
-                const int c = pass * 32 + tx;
-                bool hole = false;
-                if (pass == 0 || tx < 4) {
-                    const int gx = tx0 - 2 + c;
-                    const bool inside = row_ok && gx >= 0 && gx < W;
-                    T v = (T)CUDART_NAN;
-                    if (inside) v = KeyTraits<Key>::decode(row[gx]);
-                    s_raw[r * TS + c] = v;
-                    s_fill[r * TS + c] = (float)v;  // produce_dsm.py:58 astype(np.float32)
-                    hole = inside && row_inner && c >= 1 && c <= TILE + 2 && (v != v);
-                }
-                const unsigned m = __ballot_sync(0xffffffffu, hole);
-                if (m) {
-                    int base = 0;
-                    if (tx == 0) base = atomicAdd(&s_nholes, __popc(m));
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (hole) s_hole_pos[base + __popc(m & ((1u << tx) - 1u))] = (unsigned short)(r * TS + c);
-                }
-            }
-        }
+    // 1. decode keys (+2 halo).  Key 0 (= empty, and what is used outside the grid) decodes to NaN, and the fill
+    //    only uses in-range neighbours (:73).  Holes = empty cells inside the grid within the 1-cell halo.
+    for (int i = tid; i < TR * TR; i += kThreads) {
+        const int r = i / TR, c = i - r * TR;
+        const int gy = ty0 - 2 + r, gx = tx0 - 2 + c;
+        const bool inside = (unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W;
+        Key k = 0;
+        if (inside) k = keygrid[(size_t)gy * W + gx];
+        const T v = KeyTraits<Key>::decode(k);
+        const int pos = r * TS + c;
+        s_raw[pos] = v;
+        if (!kSameTile) s_fill[pos] = (float)v;     // produce_dsm.py:58 astype(np.float32)
+        if (inside && k == 0 && (unsigned)(r - 1) < (unsigned)(TILE + 2) && (unsigned)(c - 1) < (unsigned)(TILE + 2))
+            s_hole_pos[atomicAdd(&s_nholes, 1)] = (unsigned short)pos;
     }
     __syncthreads();
 
-    // 2. hole fill: NaN cell <- median of its non-NaN 3x3 neighbours in the PRE-fill grid (dense over the list)
+    // 2. hole fill: NaN cell <- median of its non-NaN 3x3 neighbours in the PRE-fill grid (dense over the list;
+    //    results are staged so that the fill does not cascade, lib/proj_to_grid.py:65)
     const int nholes = s_nholes;
     for (int h = tid; h < nholes; h += kThreads) {
         const T* c = s_raw + s_hole_pos[h];
@@ -196,8 +181,8 @@ k_grid_finalize(const Key* __restrict__ keygrid, int W, int H, typename KeyTrait
     for (int h = tid; h < nholes; h += kThreads) {
         const int pos = s_hole_pos[h];
         const T v = s_hole_val[h];
-        s_fill[pos] = (float)v;
-        if (filled_out != nullptr) s_raw[pos] = v;
+        s_raw[pos] = v;
+        if (!kSameTile) s_fill[pos] = (float)v;
     }
     __syncthreads();
     if (filled_out != nullptr) {

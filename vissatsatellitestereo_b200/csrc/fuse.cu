@@ -12,7 +12,7 @@
 // (the re-reads of passes 2 and 3 hit L1/L2).  Algorithmic traffic: 4V bytes read + 4 bytes written per cell.
 //
 // V <= 64: values live in registers and are sorted with a Batcher merge-exchange network (sortnets_gen.cuh),
-//          branch-free.  V > 64: per-thread quickselect on a shared-memory column (valid values compacted).
+//          branch-free.  V > 64: 8 or 32 threads per cell, sorted runs in shared memory (k_fuse_large).
 #include <math_constants.h>
 
 #include "sortnets_gen.cuh"
@@ -39,6 +39,26 @@ VS_DEF_SORTNET(48)
 VS_DEF_SORTNET(56)
 VS_DEF_SORTNET(64)
 #undef VS_DEF_SORTNET
+
+// Bitonic merge (ascending) of a bitonic sequence held in N registers; N is padded to a power of two with
+// virtual +inf wires, whose compare-exchanges are no-ops and are skipped at compile time.
+template <int N>
+__device__ __forceinline__ void bitonic_merge_regs(float (&a)[N]) {
+    constexpr int N2 = N <= 8 ? 8 : N <= 16 ? 16 : N <= 32 ? 32 : 64;
+#pragma unroll
+    for (int j = N2 / 2; j > 0; j >>= 1) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const int l = i ^ j;
+            if (l > i && l < N) {
+                const float lo = fminf(a[i], a[l]);
+                const float hi = fmaxf(a[i], a[l]);
+                a[i] = lo;
+                a[l] = hi;
+            }
+        }
+    }
+}
 
 // (s[(k-1)/2] + s[k/2]) / 2 with static register indexing
 template <int N>
@@ -107,12 +127,11 @@ k_fuse_small(const float* __restrict__ views, int64_t plane_stride, int V, int64
     }
     SortNet<NV>::sort(s);
     const float med = middle_of_sorted<NV>(s, k);
+    // |s - med| over the SORTED values falls, then rises (the +inf pads stay +inf at the end): a bitonic
+    // sequence, so one bitonic merge sorts it -- no second full sort.
 #pragma unroll
-    for (int v = 0; v < NV; ++v) {
-        const float d = fabsf(__fsub_rn(x[v], med));  // NaN stays NaN
-        s[v] = (d == d) ? d : CUDART_INF_F;
-    }
-    SortNet<NV>::sort(s);
+    for (int v = 0; v < NV; ++v) s[v] = fabsf(__fsub_rn(s[v], med));
+    bitonic_merge_regs<NV>(s);
     const float mad = middle_of_sorted<NV>(s, k);
     int cnt = 0;
 #pragma unroll
@@ -128,140 +147,214 @@ k_fuse_small(const float* __restrict__ views, int64_t plane_stride, int V, int64
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// generic path (V > 64): shared-memory column per thread, stride = blockDim.x
+// large V (65..2048): LANES threads per cell.
+//
+// 1. The CTA loads its cells x V tile with coalesced 128-byte rows into shared memory.
+// 2. Lane l of a cell takes values v = l, l+LANES, ... (<= NVL of them), sorts them in registers with the same
+//    merge-exchange network as the small path and writes them back as a sorted run of order-preserving keys.
+// 3. Order statistics of the union of the LANES runs come from a 32-step bitwise bisection on the key; each
+//    step is one branch-free lower_bound per lane (<= 7 shared-memory probes) and a shuffle reduction.
+// 4. For the MAD each lane turns its sorted run into |x - med| (bitonic), merges it in registers, and the same
+//    bisection runs on those runs.
+// 5. The float32 sum in numpy's pairwise order is accumulated by lanes 0..7 of the cell (numpy's 8 strided
+//    accumulators), re-reading the views from L2.
 // ---------------------------------------------------------------------------------------------------------
-struct SmemCol {
-    float* base;
-    int stride;
-    __device__ __forceinline__ float& operator[](int i) const { return base[i * stride]; }
-};
-
-// after the call: c[n] holds the n-th smallest of c[0..k), everything before it is <= c[n]
-__device__ __forceinline__ void quickselect(const SmemCol& c, int k, int n) {
-    int lo = 0, hi = k - 1;
-    while (hi > lo) {
-        if (hi - lo < 8) {  // insertion sort of the small remaining window
-            for (int i = lo + 1; i <= hi; ++i) {
-                const float t = c[i];
-                int j = i - 1;
-                while (j >= lo && c[j] > t) {
-                    c[j + 1] = c[j];
-                    --j;
-                }
-                c[j + 1] = t;
-            }
-            return;
-        }
-        // median-of-3 pivot
-        const int mid = lo + ((hi - lo) >> 1);
-        float a = c[lo], b = c[mid], d = c[hi];
-        if (a > b) { const float t = a; a = b; b = t; }
-        if (b > d) { const float t = b; b = d; d = t; }
-        if (a > b) { const float t = a; a = b; b = t; }
-        c[lo] = a; c[mid] = b; c[hi] = d;
-        const float pivot = b;
-        int i = lo, j = hi;
-        // Hoare partition (stops on equal keys, so runs of equal heights split evenly)
-        while (true) {
-            do { ++i; } while (c[i] < pivot);
-            do { --j; } while (c[j] > pivot);
-            if (i >= j) break;
-            const float t = c[i]; c[i] = c[j]; c[j] = t;
-        }
-        // now c[lo..j] <= pivot <= c[j+1..hi]
-        if (n <= j) hi = j; else lo = j + 1;
-    }
-}
-
-__device__ __forceinline__ float middle_by_select(const SmemCol& c, int k) {
-    const int ilo = (k - 1) >> 1, ihi = k >> 1;
-    quickselect(c, k, ihi);
-    const float hi = c[ihi];
-    float lo = hi;
-    if (ilo != ihi) {
-        lo = c[0];
-        for (int i = 1; i < ihi; ++i) lo = fmaxf(lo, c[i]);
-    }
-    return __fdiv_rn(__fadd_rn(lo, hi), 2.0f);
-}
-
 struct KeepFn {
     const float* p;
     int64_t stride;
     float med, mad;
+    __device__ __forceinline__ bool kept(int v) const {
+        const float t = __ldg(p + (int64_t)v * stride);
+        const float d = fabsf(__fsub_rn(t, med));
+        return (t == t) && !(d > mad);          // aggregate_2p5d.py:76-77
+    }
     __device__ __forceinline__ float operator()(int v) const {
         const float t = __ldg(p + (int64_t)v * stride);
         const float d = fabsf(__fsub_rn(t, med));
-        return ((t == t) && !(d > mad)) ? t : 0.0f;
+        return ((t == t) && !(d > mad)) ? t : 0.0f;   // nanmean: NaN / rejected -> +0
     }
 };
 
-__device__ __forceinline__ float pairwise_leaf_dyn(const KeepFn& y, int off, int n) {
-    if (n < 8) {
-        float res = 0.0f;
-        for (int i = 0; i < n; ++i) res = __fadd_rn(res, y(off + i));
-        return res;
-    }
-    float r[8];
+constexpr int kLargeThreads = 256;
+
+template <int LANES>
+__device__ __forceinline__ int group_sum(int v, unsigned mask) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) r[j] = y(off + j);
-    int i = 8;
-    for (; i < n - (n & 7); i += 8) {
+    for (int o = LANES / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+    return v;
+}
+template <int LANES>
+__device__ __forceinline__ uint32_t group_max(uint32_t v, unsigned mask) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(r[j], y(off + i + j));
-    }
-    float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
-                          __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
-    for (; i < n; ++i) res = __fadd_rn(res, y(off + i));
-    return res;
+    for (int o = LANES / 2; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(mask, v, o));
+    return v;
 }
 
-// numpy pairwise_sum: n > 128 -> split at n/2 rounded down to a multiple of 8
-template <int DEPTH>
-__device__ __forceinline__ float pairwise_dyn(const KeepFn& y, int off, int n) {
-    if (n <= 128) return pairwise_leaf_dyn(y, off, n);
-    int n2 = n >> 1;
-    n2 -= n2 & 7;
-    return __fadd_rn(pairwise_dyn<DEPTH - 1>(y, off, n2), pairwise_dyn<DEPTH - 1>(y, off + n2, n - n2));
-}
-template <>
-__device__ __forceinline__ float pairwise_dyn<0>(const KeepFn& y, int off, int n) {
-    return pairwise_leaf_dyn(y, off, n);  // unreachable for V <= 128 * 2^DEPTH (checked on the host)
-}
-constexpr int kPairwiseDepth = 5;  // V <= 4096
-
-__global__ void k_fuse_generic(const float* __restrict__ views, int64_t plane_stride, int V, int64_t n_cells,
-                               float* __restrict__ out) {
-    extern __shared__ float s_col[];
-    const int64_t cell = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (cell >= n_cells) return;
-    const SmemCol c{s_col + threadIdx.x, (int)blockDim.x};
-    const float* p = views + cell;
-    int k = 0;
-    for (int v = 0; v < V; ++v) {
-        const float t = __ldg(p + (int64_t)v * plane_stride);
-        if (t == t) c[k++] = t;
+// number of keys < T in this lane's sorted run (NVL keys, stride LANES)
+template <int LANES, int NVL>
+__device__ __forceinline__ int run_lower_bound(const uint32_t* __restrict__ run, uint32_t T) {
+    constexpr int P = NVL >= 64 ? 64 : NVL >= 32 ? 32 : NVL >= 16 ? 16 : 8;
+    int lb = 0;
+#pragma unroll
+    for (int step = P; step >= 1; step >>= 1) {
+        const int idx = lb + step;
+        if (idx <= NVL && run[(idx - 1) * LANES] < T) lb = idx;
     }
-    if (k <= 2) {
-        out[cell] = CUDART_NAN_F;
+    return lb;
+}
+
+// keys of rank r_hi and r_hi-1 (0-based) in the union of the group's runs; k_lo_out = k_hi if want_lo is false
+template <int LANES, int NVL>
+__device__ __forceinline__ void group_select(const uint32_t* __restrict__ run, int r_hi, bool want_lo, unsigned mask,
+                                             uint32_t start_key, int start_bit, uint32_t& k_hi_out, uint32_t& k_lo_out) {
+    uint32_t K = start_key;
+    for (int b = start_bit; b >= 0; --b) {  // largest K with count(keys < K) <= r_hi  ==  the r_hi-th smallest key
+        const uint32_t T = K | (1u << b);
+        const int c = group_sum<LANES>(run_lower_bound<LANES, NVL>(run, T), mask);
+        if (c <= r_hi) K = T;
+    }
+    k_hi_out = K;
+    k_lo_out = K;
+    if (want_lo) {
+        const int lb = run_lower_bound<LANES, NVL>(run, K);
+        const int below = group_sum<LANES>(lb, mask);
+        if (below == r_hi) {  // rank r_hi-1 is the largest key below K
+            const uint32_t mine = lb > 0 ? run[(lb - 1) * LANES] : 0u;
+            k_lo_out = group_max<LANES>(mine, mask);
+        }
+    }
+}
+
+template <int LANES, int NVL>
+__global__ void __launch_bounds__(kLargeThreads)
+k_fuse_large(const float* __restrict__ views, int64_t plane_stride, int V, int64_t n_cells, int VS,
+             float* __restrict__ out) {
+    constexpr int CELLS = kLargeThreads / LANES;  // cells per CTA
+    extern __shared__ uint32_t s_tile[];          // CELLS x VS words: floats first, then keys
+    const int tid = threadIdx.x;
+    const int64_t cell0 = blockIdx.x * (int64_t)CELLS;
+
+    // 1. coalesced load: consecutive threads read consecutive cells of one view plane
+    for (int i = tid; i < CELLS * V; i += kLargeThreads) {
+        const int v = i / CELLS, c = i - v * CELLS;
+        const int64_t cell = cell0 + c;
+        float t = CUDART_NAN_F;
+        if (cell < n_cells) t = __ldg(views + (int64_t)v * plane_stride + cell);
+        s_tile[c * VS + v] = __float_as_uint(t);
+    }
+    __syncthreads();
+
+    const int c_local = tid / LANES, lane = tid % LANES;
+    const int64_t cell = cell0 + c_local;
+    const unsigned gmask = LANES == 32 ? 0xffffffffu : (((1u << LANES) - 1u) << ((tid & 31) / LANES * LANES));
+    uint32_t* run = s_tile + c_local * VS + lane;  // element i of this lane's run: run[i * LANES]
+
+    // 2. per-lane sorted run
+    float s[NVL];
+    int k_lane = 0;
+#pragma unroll
+    for (int i = 0; i < NVL; ++i) {
+        const int v = lane + i * LANES;
+        float t = CUDART_INF_F;
+        if (v < V) {
+            const float x = __uint_as_float(run[i * LANES]);
+            if (x == x) {
+                t = x;
+                ++k_lane;
+            }
+        }
+        s[i] = t;
+    }
+    const int k = group_sum<LANES>(k_lane, gmask);
+    if (cell >= n_cells) return;       // whole group leaves together
+    if (k <= 2) {                      // aggregate_2p5d.py:69-71
+        if (lane == 0) out[cell] = CUDART_NAN_F;
         return;
     }
-    const float med = middle_by_select(c, k);
-    int j = 0;
-    for (int v = 0; v < V; ++v) {
-        const float t = __ldg(p + (int64_t)v * plane_stride);
-        if (t == t) c[j++] = fabsf(__fsub_rn(t, med));
-    }
-    const float mad = middle_by_select(c, k);
+    SortNet<NVL>::sort(s);
+#pragma unroll
+    for (int i = 0; i < NVL; ++i) run[i * LANES] = vs_key32(s[i]);
+    __syncwarp(gmask);
+
+    // 3. median
+    const int ilo = (k - 1) >> 1, ihi = k >> 1;
+    uint32_t khi, klo;
+    group_select<LANES, NVL>(run, ihi, ilo != ihi, gmask, 0u, 31, khi, klo);
+    const float med = __fdiv_rn(__fadd_rn(vs_unkey32(klo), vs_unkey32(khi)), 2.0f);
+    __syncwarp(gmask);
+
+    // 4. MAD: |sorted run - med| is bitonic per lane -> merge in registers -> runs of keys again
+#pragma unroll
+    for (int i = 0; i < NVL; ++i) s[i] = fabsf(__fsub_rn(s[i], med));
+    bitonic_merge_regs<NVL>(s);
+#pragma unroll
+    for (int i = 0; i < NVL; ++i) run[i * LANES] = vs_key32(s[i]);
+    __syncwarp(gmask);
+    group_select<LANES, NVL>(run, ihi, ilo != ihi, gmask, 0x80000000u, 30, khi, klo);   // deviations are >= 0
+    const float mad = __fdiv_rn(__fadd_rn(vs_unkey32(klo), vs_unkey32(khi)), 2.0f);
+
+    // 5. nanmean of the survivors in numpy's pairwise order: lane j < 8 owns accumulator r[j]
+    const KeepFn y{views + cell, plane_stride, med, mad};
+    const int j = lane & 7;
+    const bool acc_lane = lane < 8;
     int cnt = 0;
-    for (int v = 0; v < V; ++v) {
-        const float t = __ldg(p + (int64_t)v * plane_stride);
-        const float d = fabsf(__fsub_rn(t, med));
-        cnt += ((t == t) && !(d > mad));
+    float total = 0.0f;
+    {
+        // iterative walk over numpy's recursion tree (leaves of <= 128 elements, splits at multiples of 8),
+        // left to right; partial sums are combined with an explicit stack exactly as the recursion would
+        float stack_val[12];
+        int stack_lvl[12];
+        int sp = 0;
+        int seg_off[12], seg_n[12], seg_lvl[12];
+        int tp = 0;
+        seg_off[0] = 0; seg_n[0] = V; seg_lvl[0] = 0; tp = 1;
+        while (tp > 0) {
+            --tp;
+            const int off = seg_off[tp], n = seg_n[tp], lvl = seg_lvl[tp];
+            if (n > 128) {
+                int n2 = n >> 1;
+                n2 -= n2 & 7;
+                // push right first so that left is processed first
+                seg_off[tp] = off + n2; seg_n[tp] = n - n2; seg_lvl[tp] = lvl + 1; ++tp;
+                seg_off[tp] = off; seg_n[tp] = n2; seg_lvl[tp] = lvl + 1; ++tp;
+                continue;
+            }
+            // ---- leaf
+            float leaf;
+            if (n < 8) {
+                leaf = 0.0f;
+                for (int i = 0; i < n; ++i) leaf = __fadd_rn(leaf, y(off + i));   // every lane computes the same value
+            } else {
+                float r = 0.0f;
+                const int nfull = n - (n & 7);
+                if (acc_lane) {
+                    r = y(off + j);
+                    for (int i = 8; i < nfull; i += 8) r = __fadd_rn(r, y(off + i + j));
+                }
+                // ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) over lanes 0..7 of the group
+                float t = __fadd_rn(r, __shfl_xor_sync(gmask, r, 1));
+                t = __fadd_rn(t, __shfl_xor_sync(gmask, t, 2));
+                t = __fadd_rn(t, __shfl_xor_sync(gmask, t, 4));
+                leaf = __shfl_sync(gmask, t, 0, LANES);
+                for (int i = nfull; i < n; ++i) leaf = __fadd_rn(leaf, y(off + i));
+            }
+            // ---- combine with finished left siblings
+            float val = leaf;
+            int l = lvl;
+            while (sp > 0 && stack_lvl[sp - 1] == l) {
+                val = __fadd_rn(stack_val[sp - 1], val);
+                --sp;
+                --l;
+            }
+            stack_val[sp] = val;
+            stack_lvl[sp] = l;
+            ++sp;
+        }
+        total = stack_val[0];
     }
-    const KeepFn y{p, plane_stride, med, mad};
-    const float tot = pairwise_dyn<kPairwiseDepth>(y, 0, V);
-    out[cell] = __fdiv_rn(tot, (float)cnt);
+    for (int v = lane; v < V; v += LANES) cnt += y.kept(v);
+    cnt = group_sum<LANES>(cnt, gmask);
+    if (lane == 0) out[cell] = __fdiv_rn(total, (float)cnt);
 }
 
 template <int NV>
@@ -273,12 +366,37 @@ int launch_small(vs_ctx* ctx, const float* views, int64_t plane_stride, int V, i
     return VS_OK;
 }
 
+template <int LANES, int NVL>
+int launch_large_t(vs_ctx* ctx, const float* views, int64_t plane_stride, int V, int64_t n_cells, float* out,
+                   cudaStream_t stream) {
+    constexpr int CELLS = kLargeThreads / LANES;
+    int VS = LANES * NVL;
+    VS += (9 - (VS & 31) + 32) & 31;  // row stride = 9 (mod 32): conflict-free tile stores, few conflicts on the runs
+    const size_t smem = (size_t)CELLS * VS * sizeof(uint32_t);
+    VS_CUDA(cudaFuncSetAttribute(k_fuse_large<LANES, NVL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t blocks = (n_cells + CELLS - 1) / CELLS;
+    k_fuse_large<LANES, NVL><<<(unsigned)blocks, kLargeThreads, smem, stream>>>(views, plane_stride, V, n_cells, VS, out);
+    VS_CHECK_LAUNCH(ctx, "k_fuse_large");
+    return VS_OK;
+}
+
+int launch_large(vs_ctx* ctx, const float* views, int64_t plane_stride, int V, int64_t n_cells, float* out,
+                 cudaStream_t stream) {
+#define VS_TRY(LANES, NVL) \
+    if (V <= LANES * NVL) return launch_large_t<LANES, NVL>(ctx, views, plane_stride, V, n_cells, out, stream);
+    VS_TRY(8, 16) VS_TRY(8, 24) VS_TRY(8, 32) VS_TRY(8, 40) VS_TRY(8, 48) VS_TRY(8, 56) VS_TRY(8, 64)
+    VS_TRY(32, 24) VS_TRY(32, 32) VS_TRY(32, 48) VS_TRY(32, 64)
+#undef VS_TRY
+    vs_set_error("vs_fuse_views: more than 2048 views");
+    return VS_ERR_INVALID;
+}
+
 }  // namespace
 
 extern "C" int vs_fuse_views(vs_ctx* ctx, const float* views, int64_t plane_stride, int32_t n_views, int32_t rows,
                              int32_t W, float* out_mean, void* stream_) {
     VS_REQUIRE(ctx != nullptr, "vs_fuse_views: NULL context");
-    VS_REQUIRE(n_views >= 1 && n_views <= 128 * (1 << kPairwiseDepth), "vs_fuse_views: n_views must be 1..4096");
+    VS_REQUIRE(n_views >= 1 && n_views <= 2048, "vs_fuse_views: n_views must be 1..2048");
     VS_REQUIRE(rows >= 0 && W >= 0, "vs_fuse_views: negative size");
     const int64_t n_cells = (int64_t)rows * W;
     if (n_cells == 0) return VS_OK;
@@ -297,14 +415,6 @@ extern "C" int vs_fuse_views(vs_ctx* ctx, const float* views, int64_t plane_stri
     if (V <= 48) return launch_small<48>(ctx, views, plane_stride, V, n_cells, out_mean, stream);
     if (V <= 56) return launch_small<56>(ctx, views, plane_stride, V, n_cells, out_mean, stream);
     if (V <= 64) return launch_small<64>(ctx, views, plane_stride, V, n_cells, out_mean, stream);
-    // generic: one shared-memory column of V floats per thread
-    int block = 128;
-    while (block > 32 && (size_t)block * V * sizeof(float) > 200 * 1024) block >>= 1;
-    const size_t smem = (size_t)block * V * sizeof(float);
-    VS_REQUIRE(smem <= 227 * 1024, "vs_fuse_views: too many views for one shared-memory column per cell");
-    VS_CUDA(cudaFuncSetAttribute(k_fuse_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int64_t blocks = (n_cells + block - 1) / block;
-    k_fuse_generic<<<(unsigned)blocks, block, smem, stream>>>(views, plane_stride, V, n_cells, out_mean);
-    VS_CHECK_LAUNCH(ctx, "k_fuse_generic");
-    return VS_OK;
+    return launch_large(ctx, views, plane_stride, V, n_cells, out_mean, stream);
 }
+

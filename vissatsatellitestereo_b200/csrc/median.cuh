@@ -36,6 +36,11 @@ __device__ __forceinline__ float vs_median3_line(float p0, float p1, float p2) {
     return p1;
 }
 
+__device__ __forceinline__ float vs_min_t(float a, float b) { return fminf(a, b); }
+__device__ __forceinline__ float vs_max_t(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ double vs_min_t(double a, double b) { return fmin(a, b); }
+__device__ __forceinline__ double vs_max_t(double a, double b) { return fmax(a, b); }
+
 // Median of the k non-NaN values among 8 candidates (lib/proj_to_grid.py:70-79 -> np.median of a list):
 // odd k -> middle element, even k -> mean of the two middle elements (computed in double, as numpy does
 // for a float64 list), k == 0 -> NaN.  T is float (32-bit key path) or double (64-bit key path).
@@ -49,7 +54,7 @@ __device__ __forceinline__ T vs_median_of_valid8(T v[8]) {
     }
     if (k == 0) return (T)CUDART_NAN;
     // Batcher odd-even merge sort for 8 inputs (19 exchanges); values are NaN-free here
-#define VS_CE(i, j) { T lo = v[i] < v[j] ? v[i] : v[j]; T hi = v[i] < v[j] ? v[j] : v[i]; v[i] = lo; v[j] = hi; }
+#define VS_CE(i, j) { const T lo = vs_min_t(v[i], v[j]); const T hi = vs_max_t(v[i], v[j]); v[i] = lo; v[j] = hi; }
     VS_CE(0, 1) VS_CE(2, 3) VS_CE(4, 5) VS_CE(6, 7)
     VS_CE(0, 2) VS_CE(1, 3) VS_CE(4, 6) VS_CE(5, 7)
     VS_CE(1, 2) VS_CE(5, 6)

@@ -78,14 +78,26 @@ __device__ __noinline__ int scatter_exact_point(const VsExactParams* __restrict_
 
 // Coefficients of the per-AOI polynomial as the kernel consumes them (kernel parameter, constant bank).
 struct PolyCoefs {
-    double c64[3][VS_MAX_TERMS];  // MIXED: degree-2 part (10 terms, degree-2 index order); else all terms
-    float c32[3][VS_MAX_TERMS];   // MIXED: terms of degree 3..D (degree-D index order, low terms zero)
+    double c64[3][VS_MAX_TERMS];  // D64 > 0: the degree-D64 part (4 or 10 terms, degree-D64 index order); else all terms
+    float c32[3][VS_MAX_TERMS];   // D64 > 0: terms of degree D64+1..D (degree-D index order, low terms zero)
 };
 
 constexpr int PX = 4;  // pixels per thread per step (one 16-byte load), evaluated in lockstep
 
-template <int D, bool MIXED>
-__global__ void __launch_bounds__(kThreads, 2)
+// fast reciprocal: hardware seed (~2^-20) + two Newton steps; |error| ~ 1 ulp, no slow-path branch.  The
+// divisor is the homogeneous coordinate of a finite camera ray (never denormal/zero for a valid pixel; a zero
+// gives inf/NaN, which the finite test below rejects like the reference's division would).
+__device__ __forceinline__ double fast_rcp(double a) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+    double e = fma(-a, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-a, r, 1.0);
+    return fma(r, e, r);
+}
+
+template <int D, int D64>
+__global__ void __launch_bounds__(kThreads, D64 == 1 ? 3 : 2)
 k_unproject_scatter(RasterParams p, PolyCoefs pc, const VsExactParams* __restrict__ ex, const float* __restrict__ depth,
                     uint32_t* __restrict__ keygrid, float* __restrict__ height_map,
                     unsigned long long* __restrict__ stats) {
@@ -150,7 +162,7 @@ k_unproject_scatter(RasterParams p, PolyCoefs pc, const VsExactParams* __restric
                 }
                 const double fc = (double)col, d = (double)d4[i];
                 const double hw = fma(p.M3[0], fc, fma(p.M3[3], d, r3));
-                const double rw = 1.0 / hw;
+                const double rw = fast_rcp(hw);
                 u[i] = fma(p.Mn[0][0], fc, fma(p.Mn[0][3], d, r0)) * rw;
                 v[i] = fma(p.Mn[1][0], fc, fma(p.Mn[1][3], d, r1)) * rw;
                 w[i] = fma(p.Mn[2][0], fc, fma(p.Mn[2][3], d, r2)) * rw;
@@ -190,8 +202,8 @@ k_unproject_scatter(RasterParams p, PolyCoefs pc, const VsExactParams* __restric
 #pragma unroll
         for (int o = 0; o < 3; ++o) {
             double val[PX];
-            if (MIXED) {
-                vs_poly_eval_n<2, PX, double>(pc.c64[o], u, v, w, val);
+            if (D64 > 0) {
+                vs_poly_eval_n<(D64 > 0 ? D64 : 1), PX, double>(pc.c64[o], u, v, w, val);
                 float hi[PX];
                 vs_poly_eval_n<D, PX, float>(pc.c32[o], uf, vf, wf, hi);
 #pragma unroll
@@ -360,9 +372,9 @@ int vs_unproject_rasterize(vs_ctx* ctx, const float* depth, int32_t H, int32_t W
     if (P.degree > 0) {
         PolyCoefs pc;
         memset(&pc, 0, sizeof(pc));
-        if (P.mixed) {
+        if (P.d64 > 0) {
             for (int o = 0; o < 3; ++o) {
-                memcpy(pc.c64[o], P.coef2[o], sizeof(P.coef2[o]));
+                memcpy(pc.c64[o], P.coefLo[o], sizeof(P.coefLo[o]));
                 memcpy(pc.c32[o], P.coefR[o], sizeof(P.coefR[o]));
             }
         } else {
@@ -370,15 +382,18 @@ int vs_unproject_rasterize(vs_ctx* ctx, const float* depth, int32_t H, int32_t W
         }
         const VsExactParams* ex = reinterpret_cast<const VsExactParams*>(ctx->d_exact);
         const int grid = persistent_grid(ctx, (n_pix + PX - 1) / PX, 8);
-#define VS_LAUNCH_K1(DEG, MIX) \
-    k_unproject_scatter<DEG, MIX><<<grid, kThreads, 0, stream>>>(p, pc, ex, depth, keygrid, height_map, d_stats)
-        switch (P.degree * 2 + (P.mixed ? 1 : 0)) {
-            case 6: VS_LAUNCH_K1(3, false); break;
-            case 7: VS_LAUNCH_K1(3, true); break;
-            case 8: VS_LAUNCH_K1(4, false); break;
-            case 9: VS_LAUNCH_K1(4, true); break;
-            case 10: VS_LAUNCH_K1(5, false); break;
-            case 11: VS_LAUNCH_K1(5, true); break;
+#define VS_LAUNCH_K1(DEG, LO) \
+    k_unproject_scatter<DEG, LO><<<grid, kThreads, 0, stream>>>(p, pc, ex, depth, keygrid, height_map, d_stats)
+        switch (P.degree * 3 + P.d64) {
+            case 9: VS_LAUNCH_K1(3, 0); break;
+            case 10: VS_LAUNCH_K1(3, 1); break;
+            case 11: VS_LAUNCH_K1(3, 2); break;
+            case 12: VS_LAUNCH_K1(4, 0); break;
+            case 13: VS_LAUNCH_K1(4, 1); break;
+            case 14: VS_LAUNCH_K1(4, 2); break;
+            case 15: VS_LAUNCH_K1(5, 0); break;
+            case 16: VS_LAUNCH_K1(5, 1); break;
+            case 17: VS_LAUNCH_K1(5, 2); break;
             default: vs_set_error("vs_unproject_rasterize: bad polynomial degree"); return VS_ERR_STATE;
         }
 #undef VS_LAUNCH_K1

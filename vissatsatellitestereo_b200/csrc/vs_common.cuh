@@ -20,10 +20,11 @@ struct VsPoly {
     double center[3];
     double inv_half[3];
     double coef[3][VS_MAX_TERMS];  // [0] = col_f, [1] = row_f, [2] = alt
-    // mixed-precision split of the same polynomial (used when `mixed`): terms of total degree <= 2 in
-    // float64 (degree-2 index order), terms of degree 3..D in float32 (degree-D index order, low terms zero)
-    int mixed;
-    double coef2[3][10];
+    // mixed-precision split of the same polynomial (used when d64 > 0): terms of total degree <= d64 (1 or 2)
+    // in float64 (degree-d64 index order), terms of degree d64+1..D in float32 (degree-D index order, low
+    // terms zero).  d64 == 0: every term in float64.
+    int d64;
+    double coefLo[3][10];
     float coefR[3][VS_MAX_TERMS];
 };
 
