@@ -29,6 +29,7 @@ struct RasterParams {
     int H, W;
     int xsize, ysize;
     int degree;
+    unsigned long long w_magic;  // ceil(2^48 / W)
 };
 
 __device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
@@ -96,103 +97,139 @@ __device__ __forceinline__ double fast_rcp(double a) {
     return fma(r, e, r);
 }
 
+// One 4-pixel chunk that does not sit inside a single image row, or the ragged tail of the image: evaluated
+// pixel by pixel through the same device functions (rare: only when W is not a multiple of 4 / at the very end).
+template <int D, int D64>
+__device__ __forceinline__ void scatter_chunk_generic(const RasterParams& p, const PolyCoefs& pc,
+                                                   const VsExactParams* __restrict__ ex, const float* __restrict__ depth,
+                                                   int64_t base, int64_t n_pix, uint32_t* __restrict__ keygrid,
+                                                   float* __restrict__ height_map, bool audit, unsigned (&cnt)[4]) {
+    for (int i = 0; i < PX; ++i) {
+        const int64_t idx = base + i;
+        if (idx >= n_pix) break;
+        const float df = depth[idx];
+        float hm = CUDART_NAN_F;
+        if (df > 0.0f) {
+            const int row = (int)(idx / p.W);
+            const int col = (int)(idx - (int64_t)row * p.W);
+            const double fc = (double)col, fr = (double)row, d = (double)df;
+            const double rw = fast_rcp(fma(p.M3[0], fc, fma(p.M3[3], d, fma(p.M3[1], fr, p.M3[2]))));
+            double u[1], v[1], w[1];
+            u[0] = fma(p.Mn[0][0], fc, fma(p.Mn[0][3], d, fma(p.Mn[0][1], fr, p.Mn[0][2]))) * rw;
+            v[0] = fma(p.Mn[1][0], fc, fma(p.Mn[1][3], d, fma(p.Mn[1][1], fr, p.Mn[1][2]))) * rw;
+            w[0] = fma(p.Mn[2][0], fc, fma(p.Mn[2][3], d, fma(p.Mn[2][1], fr, p.Mn[2][2]))) * rw;
+            float uf[1] = {(float)u[0]}, vf[1] = {(float)v[0]}, wf[1] = {(float)w[0]};
+            if (fabsf(uf[0]) < CUDART_INF_F && fabsf(vf[0]) < CUDART_INF_F && fabsf(wf[0]) < CUDART_INF_F) {
+                ++cnt[VS_STAT_VALID];
+                hm = (float)fma(w[0], p.half_z, p.center_z);
+                if (fabsf(uf[0]) <= 1.0f && fabsf(vf[0]) <= 1.0f) {
+                    if (fabsf(wf[0]) <= 1.0f) {
+                        double val[3][1];
+#pragma unroll
+                        for (int o = 0; o < 3; ++o) {
+                            if (D64 > 0) {
+                                vs_poly_eval_n<(D64 > 0 ? D64 : 1), 1, double>(pc.c64[o], u, v, w, val[o]);
+                                float hi[1];
+                                vs_poly_eval_n<D, 1, float>(pc.c32[o], uf, vf, wf, hi);
+                                val[o][0] += (double)hi[0];
+                            } else {
+                                vs_poly_eval_n<D, 1, double>(pc.c64[o], u, v, w, val[o]);
+                            }
+                        }
+                        const int ci = __double2int_rd(val[0][0]), ri = __double2int_rd(val[1][0]);
+                        if ((unsigned)ci < (unsigned)p.xsize && (unsigned)ri < (unsigned)p.ysize) {
+                            ++cnt[VS_STAT_INGRID];
+                            if (audit && (fabs(val[0][0] - rint(val[0][0])) < p.eps || fabs(val[1][0] - rint(val[1][0])) < p.eps))
+                                ++cnt[VS_STAT_AMBIGUOUS];
+                            atomicMax(keygrid + (ri * p.xsize + ci), vs_key32((float)val[2][0]));
+                        }
+                    } else {
+                        ++cnt[VS_STAT_EXACT];
+                        const int r = scatter_exact_point(ex, u[0], v[0], w[0], keygrid);
+                        cnt[VS_STAT_INGRID] += (r != 0);
+                        cnt[VS_STAT_AMBIGUOUS] += (r == 2);
+                    }
+                }
+            }
+        }
+        if (height_map != nullptr) height_map[idx] = hm;
+    }
+}
+
+// K1.  Requires n_pix < 2^32 and W < 2^16 for the multiply-shift row index (checked on the host).
 template <int D, int D64>
 __global__ void __launch_bounds__(kThreads, D64 == 1 ? 3 : 2)
 k_unproject_scatter(RasterParams p, PolyCoefs pc, const VsExactParams* __restrict__ ex, const float* __restrict__ depth,
                     uint32_t* __restrict__ keygrid, float* __restrict__ height_map,
                     unsigned long long* __restrict__ stats) {
     const int64_t n_pix = (int64_t)p.H * p.W;
-    const int64_t n_chunks = (n_pix + PX - 1) / PX;
+    const unsigned n_chunks = (unsigned)((n_pix + PX - 1) / PX);
     const bool audit = stats != nullptr;
-    unsigned n_valid = 0, n_ingrid = 0, n_amb = 0, n_exact = 0;
+    const bool want_hm = height_map != nullptr;
+    unsigned cnt[4] = {0, 0, 0, 0};
 
-    for (int64_t chunk = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; chunk < n_chunks;
-         chunk += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t base = chunk * PX;
-        float d4[PX];
-        if (base + PX - 1 < n_pix) {
-            const float4 t = ld_stream_f4(reinterpret_cast<const float4*>(depth + base));
-            d4[0] = t.x; d4[1] = t.y; d4[2] = t.z; d4[3] = t.w;
-        } else {
-#pragma unroll
-            for (int i = 0; i < PX; ++i) d4[i] = (base + i < n_pix) ? depth[base + i] : -1.0f;
-        }
-        // aggregate_2p5d_util.py:76: depth <= 0 (and NaN) is invalid
-        bool ok[PX];
-        bool any_ok = false;
-#pragma unroll
-        for (int i = 0; i < PX; ++i) {
-            ok[i] = d4[i] > 0.0f;
-            any_ok |= ok[i];
-        }
-        if (!any_ok) {
-            if (height_map != nullptr) {
-#pragma unroll
-                for (int i = 0; i < PX; ++i)
-                    if (base + i < n_pix) height_map[base + i] = CUDART_NAN_F;
-            }
+    for (unsigned chunk = blockIdx.x * blockDim.x + threadIdx.x; chunk < n_chunks; chunk += gridDim.x * blockDim.x) {
+        const unsigned base = chunk * PX;
+        // row = base / W by multiply-shift (magic = ceil(2^48 / W), exact for base < 2^32, W < 2^16)
+        const unsigned row0 = (unsigned)(((unsigned long long)base * p.w_magic) >> 48);
+        const unsigned col0 = base - row0 * (unsigned)p.W;
+        if (col0 + PX > (unsigned)p.W || (int64_t)base + PX > n_pix) {   // straddles rows / ragged tail (rare)
+            scatter_chunk_generic<D, D64>(p, pc, ex, depth, base, n_pix, keygrid, height_map, audit, cnt);
             continue;
         }
-        const int row0 = (int)(base / p.W);
-        const int col0 = (int)(base - (int64_t)row0 * p.W);
+        const float4 t4 = ld_stream_f4(reinterpret_cast<const float4*>(depth + base));
+        const float d4[PX] = {t4.x, t4.y, t4.z, t4.w};
+        // aggregate_2p5d_util.py:76: depth <= 0 (and NaN) is invalid
+        if (!(d4[0] > 0.0f || d4[1] > 0.0f || d4[2] > 0.0f || d4[3] > 0.0f)) {
+            if (want_hm)
+                *reinterpret_cast<float4*>(height_map + base) =
+                    make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F);
+            continue;
+        }
 
-        // ---- aggregate_2p5d_util.py:86-90: X = M . [col, row, 1, depth]; (u, v, w) = box-normalised X/X_3
+        // ---- aggregate_2p5d_util.py:86-90: X = M . [col, row, 1, depth]; (u, v, w) = box-normalised X / X_3
         double u[PX], v[PX], w[PX];
         {
-            const bool one_row = col0 + PX <= p.W;
-            const double fr0 = (double)row0;
-            double rt[4];  // M[k][1]*row + M[k][2], shared by the pixels of one image row
-            rt[0] = fma(p.Mn[0][1], fr0, p.Mn[0][2]);
-            rt[1] = fma(p.Mn[1][1], fr0, p.Mn[1][2]);
-            rt[2] = fma(p.Mn[2][1], fr0, p.Mn[2][2]);
-            rt[3] = fma(p.M3[1], fr0, p.M3[2]);
+            const double fr = (double)row0;
+            const double fc0 = (double)col0;
+            const double r0 = fma(p.Mn[0][1], fr, p.Mn[0][2]), r1 = fma(p.Mn[1][1], fr, p.Mn[1][2]);
+            const double r2 = fma(p.Mn[2][1], fr, p.Mn[2][2]), r3 = fma(p.M3[1], fr, p.M3[2]);
 #pragma unroll
             for (int i = 0; i < PX; ++i) {
-                double r0 = rt[0], r1 = rt[1], r2 = rt[2], r3 = rt[3];
-                int col = col0 + i;
-                if (!one_row && col >= p.W) {  // chunk straddles image rows (W not a multiple of 4)
-                    const int64_t idx = base + i;
-                    const int row = (int)(idx / p.W);
-                    col = (int)(idx - (int64_t)row * p.W);
-                    const double fr = (double)row;
-                    r0 = fma(p.Mn[0][1], fr, p.Mn[0][2]);
-                    r1 = fma(p.Mn[1][1], fr, p.Mn[1][2]);
-                    r2 = fma(p.Mn[2][1], fr, p.Mn[2][2]);
-                    r3 = fma(p.M3[1], fr, p.M3[2]);
-                }
-                const double fc = (double)col, d = (double)d4[i];
-                const double hw = fma(p.M3[0], fc, fma(p.M3[3], d, r3));
-                const double rw = fast_rcp(hw);
+                const double fc = fc0 + (double)i;   // exact
+                const double d = (double)d4[i];
+                const double rw = fast_rcp(fma(p.M3[0], fc, fma(p.M3[3], d, r3)));
                 u[i] = fma(p.Mn[0][0], fc, fma(p.Mn[0][3], d, r0)) * rw;
                 v[i] = fma(p.Mn[1][0], fc, fma(p.Mn[1][3], d, r1)) * rw;
                 w[i] = fma(p.Mn[2][0], fc, fma(p.Mn[2][3], d, r2)) * rw;
             }
         }
-        // ---- classification on float32 copies (the box has a margin, so float32 rounding at its faces is
-        // harmless; a non-finite position fails every test, aggregate_2p5d_util.py:92 / proj_to_grid.py:48)
+        // ---- classification on float32 copies.  |x| <= 1 is false for NaN/inf, so a non-finite position is
+        // never "in the box" (aggregate_2p5d_util.py:92 / lib/proj_to_grid.py:48); the box has a margin around
+        // the grid, so float32 rounding at its faces is harmless.
         float uf[PX], vf[PX], wf[PX];
-        bool in_box[PX], in_alt[PX];
-        float hm[PX];
+        bool fast[PX];
+        bool any_slow = false;
 #pragma unroll
         for (int i = 0; i < PX; ++i) {
             uf[i] = (float)u[i];
             vf[i] = (float)v[i];
             wf[i] = (float)w[i];
-            const bool finite = fabsf(uf[i]) < CUDART_INF_F && fabsf(vf[i]) < CUDART_INF_F && fabsf(wf[i]) < CUDART_INF_F;
-            ok[i] = ok[i] && finite;
-            in_box[i] = ok[i] && fabsf(uf[i]) <= 1.0f && fabsf(vf[i]) <= 1.0f;  // outside the box => outside the grid
-            in_alt[i] = fabsf(wf[i]) <= 1.0f;
-            n_valid += ok[i];
-            hm[i] = ok[i] ? (float)fma(w[i], p.half_z, p.center_z) : CUDART_NAN_F;
+            const bool in_box = d4[i] > 0.0f && fabsf(uf[i]) <= 1.0f && fabsf(vf[i]) <= 1.0f;
+            const bool in_alt = fabsf(wf[i]) <= 1.0f;
+            fast[i] = in_box && in_alt;
+            any_slow |= in_box && !in_alt;
         }
-        if (height_map != nullptr) {
-            if (base + PX - 1 < n_pix) {
-                *reinterpret_cast<float4*>(height_map + base) = make_float4(hm[0], hm[1], hm[2], hm[3]);
-            } else {
+        if (audit || want_hm) {   // block-uniform
+            float hm[PX];
 #pragma unroll
-                for (int i = 0; i < PX; ++i)
-                    if (base + i < n_pix) height_map[base + i] = hm[i];
+            for (int i = 0; i < PX; ++i) {
+                const bool finite = d4[i] > 0.0f && fabsf(uf[i]) < CUDART_INF_F && fabsf(vf[i]) < CUDART_INF_F &&
+                                    fabsf(wf[i]) < CUDART_INF_F;
+                cnt[VS_STAT_VALID] += finite;
+                hm[i] = finite ? (float)fma(w[i], p.half_z, p.center_z) : CUDART_NAN_F;
             }
+            if (want_hm) *reinterpret_cast<float4*>(height_map + base) = make_float4(hm[0], hm[1], hm[2], hm[3]);
         }
 
         // ---- ENU -> (fractional col, fractional row, altitude): the per-AOI polynomial, 4 pixels in lockstep
@@ -226,35 +263,42 @@ k_unproject_scatter(RasterParams p, PolyCoefs pc, const VsExactParams* __restric
             }
         }
 
-        // ---- lib/proj_to_grid.py:44-61: bounds mask + per-cell max; same-cell neighbours merge in registers
-        int pend_cell = -1;
-        uint32_t pend_key = 0;
+        // ---- lib/proj_to_grid.py:44-61: bounds mask + per-cell max.  Same-cell neighbours merge in registers
+        // (forward chain), everything predicated.
+        int cell[PX];
 #pragma unroll
         for (int i = 0; i < PX; ++i) {
-            if (!in_box[i]) continue;
-            if (in_alt[i]) {
-                if ((unsigned)ci[i] < (unsigned)p.xsize && (unsigned)ri[i] < (unsigned)p.ysize) {
-                    ++n_ingrid;
-                    if (audit) n_amb += amb[i];
-                    const int cell = ri[i] * p.xsize + ci[i];
-                    if (cell == pend_cell) {
-                        pend_key = max(pend_key, key[i]);
-                    } else {
-                        if (pend_cell >= 0) atomicMax(keygrid + pend_cell, pend_key);
-                        pend_cell = cell;
-                        pend_key = key[i];
-                    }
-                }
-            } else {  // outside the fitted altitude range: exact chain, out of line (rare)
-                ++n_exact;
-                const int r = scatter_exact_point(ex, u[i], v[i], w[i], keygrid);
-                n_ingrid += (r != 0);
-                n_amb += (r == 2);
+            fast[i] = fast[i] && (unsigned)ci[i] < (unsigned)p.xsize && (unsigned)ri[i] < (unsigned)p.ysize;
+            cell[i] = ri[i] * p.xsize + ci[i];
+            if (audit) {
+                cnt[VS_STAT_INGRID] += fast[i];
+                cnt[VS_STAT_AMBIGUOUS] += fast[i] && amb[i];
             }
         }
-        if (pend_cell >= 0) atomicMax(keygrid + pend_cell, pend_key);
+#pragma unroll
+        for (int i = 0; i + 1 < PX; ++i) {
+            const bool same = fast[i] && fast[i + 1] && cell[i] == cell[i + 1];
+            key[i + 1] = same ? max(key[i + 1], key[i]) : key[i + 1];
+            fast[i] = fast[i] && !same;
+        }
+#pragma unroll
+        for (int i = 0; i < PX; ++i)
+            if (fast[i]) atomicMax(keygrid + cell[i], key[i]);
+
+        if (any_slow) {  // points outside the fitted altitude range: exact chain, out of line (rare)
+#pragma unroll
+            for (int i = 0; i < PX; ++i) {
+                if (d4[i] > 0.0f && fabsf(uf[i]) <= 1.0f && fabsf(vf[i]) <= 1.0f && !(fabsf(wf[i]) <= 1.0f) &&
+                    fabsf(wf[i]) < CUDART_INF_F) {
+                    ++cnt[VS_STAT_EXACT];
+                    const int r = scatter_exact_point(ex, u[i], v[i], w[i], keygrid);
+                    cnt[VS_STAT_INGRID] += (r != 0);
+                    cnt[VS_STAT_AMBIGUOUS] += (r == 2);
+                }
+            }
+        }
     }
-    flush_stats(stats, n_valid, n_ingrid, n_amb, n_exact);
+    flush_stats(stats, cnt[0], cnt[1], cnt[2], cnt[3]);
 }
 
 // Exact chain for every pixel (polynomial disabled: vs_set_aoi(max_degree = 0) or a fit that failed validation).
@@ -339,6 +383,7 @@ int vs_unproject_rasterize(vs_ctx* ctx, const float* depth, int32_t H, int32_t W
         return VS_ERR_STATE;
     }
     VS_REQUIRE(H >= 0 && W >= 0, "vs_unproject_rasterize: negative image size");
+    VS_REQUIRE(W < 65536 && (int64_t)H * W < ((int64_t)1 << 32) - 8, "vs_unproject_rasterize: image too large (W < 65536, H*W < 2^32)");
     VS_REQUIRE(M != nullptr && keygrid != nullptr, "vs_unproject_rasterize: NULL argument");
     VS_REQUIRE(((uintptr_t)depth & 15) == 0, "vs_unproject_rasterize: depth must be 16-byte aligned");
     VS_REQUIRE(height_map == nullptr || ((uintptr_t)height_map & 15) == 0,
@@ -367,6 +412,7 @@ int vs_unproject_rasterize(vs_ctx* ctx, const float* depth, int32_t H, int32_t W
     p.xsize = ctx->aoi.xsize;
     p.ysize = ctx->aoi.ysize;
     p.degree = P.degree;
+    p.w_magic = W > 0 ? (((1ull << 48) + (unsigned long long)W - 1) / (unsigned long long)W) : 0;
 
     VsEllipsoidConsts c = vs_make_ellipsoid_consts();
     if (P.degree > 0) {
