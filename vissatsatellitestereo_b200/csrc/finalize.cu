@@ -1,11 +1,17 @@
 // Stage B kernels: key grid -> per-view DSM, and the stand-alone 3x3 median.
 //
-// K2  k_grid_finalize<Key,T>   lib/proj_to_grid.py:62-79 (decode, NaN-hole fill from the PRE-fill grid) fused
-//     with produce_dsm.py:58 (astype(float32) + cv2.medianBlur(.,3)).  One CTA per 32x32 output tile; the
-//     decoded tile (+2 halo) and the hole-filled tile (+1 halo) live in shared memory, so each key is read
-//     from global memory once per tile (halo re-reads are L2 hits) and each output is written once:
-//     algorithmic traffic 4 B read + 4 B write per cell.
-// K4  k_median3x3              aggregate_2p5d.py:81 on a row band (halo rows supplied by the caller).
+// K2  k_grid_finalize<Key>   lib/proj_to_grid.py:62-79 (decode, NaN-hole fill from the PRE-fill grid) fused with
+//     produce_dsm.py:58 (astype(float32) + cv2.medianBlur(.,3)).  One CTA (256 threads) per 64x32 output tile.
+//     The decoded tile with a 2-cell halo lives in shared memory, so each key is read from global memory once
+//     per tile (halo re-reads are L2 hits) and each output is written once (16-byte stores): algorithmic traffic
+//     4 B read + 4 B write per cell.  The kernel is bound by the ALU pipe (min/max and integer instructions
+//     issue at half rate on sm_100), so the work per cell is what is optimised:
+//       * holes are listed with one shared-memory atomic each and filled densely by the first n_holes threads;
+//       * every thread blurs a 4-wide x 2-tall patch: 6 sorted 3-columns are shared by 4 windows
+//         (21 min/max per output instead of 30), rows are fetched with 16-byte shared-memory loads;
+//       * a tile without any NaN left skips every NaN test; otherwise each window with a NaN goes through the
+//         exact emulation of OpenCV's 19-exchange network (SIMD / scalar column semantics).
+// K4  k_median3x3            aggregate_2p5d.py:81 on a row band (halo rows supplied by the caller); same blur.
 #include <math_constants.h>
 
 #include "median.cuh"
@@ -13,8 +19,15 @@
 
 namespace {
 
-constexpr int TILE = 32;
+constexpr int TW = 64;            // tile width  (outputs)
+constexpr int TH = 32;            // tile height (outputs)
 constexpr int kThreads = 256;
+constexpr int OFF = 3;            // column offset of the tile inside a shared row: makes the 6-float window of a
+                                  // 4-wide patch start on a 16-byte boundary
+constexpr int TS = 72;            // shared row stride in elements (>= OFF + TW + 4, multiple of 4)
+constexpr int TR = TH + 4;        // shared rows (halo 2)
+constexpr int TC = TW + 4;        // shared columns in use (halo 2)
+constexpr int MAX_HOLES = (TH + 2) * (TW + 2);
 
 template <typename Key> struct KeyTraits;
 template <> struct KeyTraits<uint32_t> {
@@ -29,7 +42,7 @@ template <> struct KeyTraits<unsigned long long> {
 __device__ __forceinline__ void block_count_flush(unsigned local, unsigned long long* counter) {
     if (counter == nullptr) return;
     __shared__ unsigned s_cnt;
-    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    const int tid = threadIdx.x;
     if (tid == 0) s_cnt = 0;
     __syncthreads();
     unsigned r = __reduce_add_sync(0xffffffffu, local);
@@ -38,158 +51,200 @@ __device__ __forceinline__ void block_count_flush(unsigned local, unsigned long 
     if (tid == 0 && s_cnt) atomicAdd(counter, (unsigned long long)s_cnt);
 }
 
-// ---- 3x3 median on a shared-memory tile ----------------------------------------------------------------------
-// For a window without NaN every correct median algorithm returns the same value as OpenCV's network, so the
-// common case uses a cheap one (sort the three columns, then med3(max of minima, med3 of medians, min of
-// maxima): 30 min/max).  Windows that contain a NaN go through the exact emulation of OpenCV's network.
+// ---- 3x3 median pieces ----------------------------------------------------------------------------------------
+struct Col3 {
+    float lo, mid, hi;
+};
+__device__ __forceinline__ Col3 sort_col3(float a, float b, float c) {
+    Col3 r;
+    const float ab_lo = fminf(a, b), ab_hi = fmaxf(a, b);
+    r.lo = fminf(ab_lo, c);
+    r.hi = fmaxf(ab_hi, c);
+    r.mid = fmaxf(ab_lo, fminf(ab_hi, c));
+    return r;
+}
 __device__ __forceinline__ float med3f(float a, float b, float c) {
     return fmaxf(fminf(a, b), fminf(fmaxf(a, b), c));
 }
-
-__device__ __forceinline__ float median9_fast(float p0, float p1, float p2, float p3, float p4, float p5, float p6,
-                                              float p7, float p8) {
-    // columns (p0,p3,p6) (p1,p4,p7) (p2,p5,p8)
-    const float a_lo = fminf(fminf(p0, p3), p6), a_hi = fmaxf(fmaxf(p0, p3), p6), a_mid = med3f(p0, p3, p6);
-    const float b_lo = fminf(fminf(p1, p4), p7), b_hi = fmaxf(fmaxf(p1, p4), p7), b_mid = med3f(p1, p4, p7);
-    const float c_lo = fminf(fminf(p2, p5), p8), c_hi = fmaxf(fmaxf(p2, p5), p8), c_mid = med3f(p2, p5, p8);
-    return med3f(fmaxf(fmaxf(a_lo, b_lo), c_lo), med3f(a_mid, b_mid, c_mid), fminf(fminf(a_hi, b_hi), c_hi));
+// median of 9 from three sorted columns: med3(max of minima, med3 of medians, min of maxima)
+__device__ __forceinline__ float median_of_cols(const Col3& a, const Col3& b, const Col3& c) {
+    return med3f(fmaxf(fmaxf(a.lo, b.lo), c.lo), med3f(a.mid, b.mid, c.mid), fminf(fminf(a.hi, b.hi), c.hi));
+}
+__device__ __forceinline__ bool has_nan9(const float (&r0)[3], const float (&r1)[3], const float (&r2)[3]) {
+    const float sum = ((r0[0] + r0[1]) + (r0[2] + r1[0])) + ((r1[1] + r1[2]) + (r2[0] + r2[1])) + r2[2];
+    return !(sum == sum);   // NaN (or +inf with -inf): take the exact path
+}
+__device__ __forceinline__ float median9_exact(const float* r0, const float* r1, const float* r2, bool simd) {
+    return simd ? vs_median9_net<true>(r0[0], r0[1], r0[2], r1[0], r1[1], r1[2], r2[0], r2[1], r2[2])
+                : vs_median9_net<false>(r0[0], r0[1], r0[2], r1[0], r1[1], r1[2], r2[0], r2[1], r2[2]);
 }
 
-// s points at the window centre inside a tile with row stride S whose halo already holds the replicated
-// border (so no clamping here).  CHECK_NAN: test the window and fall back to the exact network.
-template <int S, bool CHECK_NAN>
-__device__ __forceinline__ float median9_tile(const float* __restrict__ s, bool simd) {
-    const float p0 = s[-S - 1], p1 = s[-S], p2 = s[-S + 1];
-    const float p3 = s[-1], p4 = s[0], p5 = s[1];
-    const float p6 = s[S - 1], p7 = s[S], p8 = s[S + 1];
-    if (CHECK_NAN) {
-        const float sum = ((p0 + p1) + (p2 + p3)) + ((p4 + p5) + (p6 + p7)) + p8;
-        if (!(sum == sum)) {  // a NaN (or +inf and -inf) in the window: exact OpenCV semantics
-            return simd ? vs_median9_net<true>(p0, p1, p2, p3, p4, p5, p6, p7, p8)
-                        : vs_median9_net<false>(p0, p1, p2, p3, p4, p5, p6, p7, p8);
-        }
-    }
-    return median9_fast(p0, p1, p2, p3, p4, p5, p6, p7, p8);
-}
-
-constexpr int TS = TILE + 5;  // row stride of the shared tiles (36 columns + 1 pad)
-constexpr int TR = TILE + 4;  // rows of the shared tiles (halo 2)
-
-// Blur phase shared by K2 and K4.  s_fill: TR x TS tile whose cell (r, c) is grid cell (ty0 - 2 + r, tx0 - 2 + c);
-// rows/columns 1..34 must be final (hole-filled) and, outside the grid, replicated from the nearest inside cell.
-// blockDim = (32, 8).  Writes out[(gy - out_row0) * W + gx] for gy in [ty0, min(ty0 + 32, row_limit)).
+// Blur phase shared by K2 and K4.  s_fill: TR x TS tile; element (r, OFF + c) is grid cell (ty0 - 2 + r, tx0 - 2 + c).
+// Rows/columns within the 1-cell halo must be final (hole-filled) and, outside the grid, replicated from the
+// nearest inside cell.  Writes out[(gy - out_row0) * W + gx] for gy in [ty0, min(ty0 + TH, row_limit)).
 __device__ __forceinline__ unsigned blur_tile(const float* __restrict__ s_fill, int ty0, int tx0, int H, int W,
                                               int row_limit, bool tile_has_nan, bool simd_cols,
                                               float* __restrict__ out, int out_row0) {
-    const int tx = threadIdx.x, ty = threadIdx.y;
-    const int gx = tx0 + tx;
+    const int tid = threadIdx.x;
     unsigned n_nan = 0;
-    if (H == 1 || W == 1) {  // OpenCV's 1-D special case (block-uniform)
-#pragma unroll
-        for (int k = 0; k < TILE / 8; ++k) {
-            const int r = ty + 8 * k, gy = ty0 + r;
+    if (H == 1 || W == 1) {  // OpenCV's 1-D special case (block-uniform): 3-tap median along the line
+        for (int i = tid; i < TW * TH; i += kThreads) {
+            const int r = i / TW, c = i - r * TW;
+            const int gy = ty0 + r, gx = tx0 + c;
             if (gy < row_limit && gx < W) {
-                const float* c = s_fill + (r + 2) * TS + (tx + 2);
-                const float m = (H == 1) ? vs_median3_line(c[-1], c[0], c[1]) : vs_median3_line(c[-TS], c[0], c[TS]);
+                const float* p = s_fill + (r + 2) * TS + (OFF + c + 2);
+                const float m = (H == 1) ? vs_median3_line(p[-1], p[0], p[1]) : vs_median3_line(p[-TS], p[0], p[TS]);
                 out[(size_t)(gy - out_row0) * W + gx] = m;
                 n_nan += (m != m);
             }
         }
         return n_nan;
     }
-    const bool simd = simd_cols && gx >= 1 && gx <= W - 2;
+    // patch of 4 columns x 2 rows per thread
+    const int k = tid & 15, rp = tid >> 4;          // strip 0..15, row pair 0..15
+    const int r = 2 * rp, c = 4 * k;
+    const int gy = ty0 + r, gx = tx0 + c;
+    if (gy >= row_limit || gx >= W) return 0;
+    // rows r-1 .. r+2 of the tile, columns c-1 .. c+4  ->  shared rows r+1 .. r+4, columns OFF+c+1 .. OFF+c+6
+    float win[4][6];
 #pragma unroll
-    for (int k = 0; k < TILE / 8; ++k) {
-        const int r = ty + 8 * k, gy = ty0 + r;
-        if (gy < row_limit && gx < W) {
-            const float* c = s_fill + (r + 2) * TS + (tx + 2);
-            const float m = tile_has_nan ? median9_tile<TS, true>(c, simd) : median9_tile<TS, false>(c, simd);
-            out[(size_t)(gy - out_row0) * W + gx] = m;
-            n_nan += (m != m);
+    for (int j = 0; j < 4; ++j) {
+        const float* p = s_fill + (r + 1 + j) * TS + (OFF + c + 1);   // 16-byte aligned
+        const float4 a = *reinterpret_cast<const float4*>(p);
+        const float2 b = *reinterpret_cast<const float2*>(p + 4);
+        win[j][0] = a.x; win[j][1] = a.y; win[j][2] = a.z; win[j][3] = a.w; win[j][4] = b.x; win[j][5] = b.y;
+    }
+    float res[2][4];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        Col3 col[6];
+#pragma unroll
+        for (int x = 0; x < 6; ++x) col[x] = sort_col3(win[j][x], win[j + 1][x], win[j + 2][x]);
+#pragma unroll
+        for (int x = 0; x < 4; ++x) res[j][x] = median_of_cols(col[x], col[x + 1], col[x + 2]);
+    }
+    if (tile_has_nan) {  // block-uniform; rare
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                const float r0[3] = {win[j][x], win[j][x + 1], win[j][x + 2]};
+                const float r1[3] = {win[j + 1][x], win[j + 1][x + 1], win[j + 1][x + 2]};
+                const float r2[3] = {win[j + 2][x], win[j + 2][x + 1], win[j + 2][x + 2]};
+                if (has_nan9(r0, r1, r2)) {
+                    const int x_g = gx + x;
+                    res[j][x] = median9_exact(r0, r1, r2, simd_cols && x_g >= 1 && x_g <= W - 2);
+                }
+            }
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int y_g = gy + j;
+        if (y_g < row_limit) {
+            float* o = out + (size_t)(y_g - out_row0) * W + gx;
+            if (gx + 3 < W && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+                *reinterpret_cast<float4*>(o) = make_float4(res[j][0], res[j][1], res[j][2], res[j][3]);
+#pragma unroll
+                for (int x = 0; x < 4; ++x) n_nan += (res[j][x] != res[j][x]);
+            } else {
+#pragma unroll
+                for (int x = 0; x < 4; ++x)
+                    if (gx + x < W) {
+                        o[x] = res[j][x];
+                        n_nan += (res[j][x] != res[j][x]);
+                    }
+            }
         }
     }
     return n_nan;
 }
 
 // Replicate the grid border into the part of the tile's 1-cell halo that lies outside the grid
-// (cv2 BORDER_REPLICATE).  Only tiles touching the grid border have such cells.  rows_lo/rows_hi: first/last grid
-// row that is valid to read (K4 row bands), normally 0 and H-1.
+// (cv2 BORDER_REPLICATE).  Only tiles touching the grid border have such cells.
 __device__ __forceinline__ void replicate_border(float* __restrict__ s_fill, int ty0, int tx0, int H, int W) {
-    if (ty0 > 0 && tx0 > 0 && ty0 + TILE < H && tx0 + TILE < W) return;  // interior tile (block-uniform)
-    const int tid = threadIdx.y * 32 + threadIdx.x;
-    for (int i = tid; i < (TILE + 2) * (TILE + 2); i += kThreads) {
-        const int r = 1 + i / (TILE + 2), c = 1 + i % (TILE + 2);
+    if (ty0 > 0 && tx0 > 0 && ty0 + TH < H && tx0 + TW < W) return;  // interior tile (block-uniform)
+    for (int i = threadIdx.x; i < (TH + 2) * (TW + 2); i += kThreads) {
+        const int r = 1 + i / (TW + 2), c = 1 + i % (TW + 2);
         const int gy = ty0 - 2 + r, gx = tx0 - 2 + c;
         if (gy < 0 || gy >= H || gx < 0 || gx >= W) {
             const int cy = min(max(gy, 0), H - 1), cx = min(max(gx, 0), W - 1);
             const int rr = cy - (ty0 - 2), cc = cx - (tx0 - 2);
-            if (rr >= 1 && rr <= TILE + 2 && cc >= 1 && cc <= TILE + 2) s_fill[r * TS + c] = s_fill[rr * TS + cc];
+            if (rr >= 1 && rr <= TH + 2 && cc >= 1 && cc <= TW + 2) s_fill[r * TS + OFF + c] = s_fill[rr * TS + OFF + cc];
         }
     }
 }
 
-// blockDim = (32, 8); one CTA per 32x32 output tile.
 template <typename Key>
 __global__ void __launch_bounds__(kThreads)
 k_grid_finalize(const Key* __restrict__ keygrid, int W, int H, typename KeyTraits<Key>::value_t* __restrict__ filled_out,
                 float* __restrict__ blur_out, int simd_cols, unsigned long long* __restrict__ nan_count) {
     typedef typename KeyTraits<Key>::value_t T;
     constexpr bool kSameTile = sizeof(T) == sizeof(float);   // float32 keys: one tile serves fill and blur
-    __shared__ T s_raw[TR * TS];                    // decoded keys; holes are patched in place after phase 2
-    __shared__ float s_fill32[kSameTile ? 1 : TR * TS];   // float32 copy (what cv2.medianBlur sees) for the f64 path
-    __shared__ unsigned short s_hole_pos[(TILE + 2) * (TILE + 2)];
-    __shared__ T s_hole_val[(TILE + 2) * (TILE + 2)];
+    __shared__ __align__(16) T s_raw[TR * TS];              // decoded keys; holes are patched in place after phase 2
+    __shared__ __align__(16) float s_fill32[kSameTile ? 4 : TR * TS];  // float32 copy for the f64 path
+    __shared__ unsigned short s_hole_pos[MAX_HOLES];
+    __shared__ float s_hole_val[kSameTile ? MAX_HOLES : 1];
     __shared__ int s_nholes, s_has_nan;
     float* s_fill = kSameTile ? reinterpret_cast<float*>(s_raw) : s_fill32;
-    const int tx = threadIdx.x, ty = threadIdx.y;
-    const int tid = ty * 32 + tx;
-    const int tx0 = blockIdx.x * TILE, ty0 = blockIdx.y * TILE;
+    const int tid = threadIdx.x;
+    const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH;
     if (tid == 0) {
         s_nholes = 0;
         s_has_nan = 0;
     }
     __syncthreads();
 
-    // 1. decode keys (+2 halo).  Key 0 (= empty, and what is used outside the grid) decodes to NaN, and the fill
-    //    only uses in-range neighbours (:73).  Holes = empty cells inside the grid within the 1-cell halo.
-    for (int i = tid; i < TR * TR; i += kThreads) {
-        const int r = i / TR, c = i - r * TR;
+    // 1. decode keys (+2 halo).  Key 0 (= empty, also used outside the grid) decodes to NaN, and the fill only
+    //    uses in-range neighbours (:73).  Holes = empty cells inside the grid within the 1-cell halo.
+    for (int i = tid; i < TR * TC; i += kThreads) {
+        const int r = i / TC, c = i - r * TC;
         const int gy = ty0 - 2 + r, gx = tx0 - 2 + c;
         const bool inside = (unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W;
-        Key k = 0;
-        if (inside) k = keygrid[(size_t)gy * W + gx];
-        const T v = KeyTraits<Key>::decode(k);
-        const int pos = r * TS + c;
+        Key key = 0;
+        if (inside) key = keygrid[(size_t)gy * W + gx];
+        const T v = KeyTraits<Key>::decode(key);
+        const int pos = r * TS + OFF + c;
         s_raw[pos] = v;
         if (!kSameTile) s_fill[pos] = (float)v;     // produce_dsm.py:58 astype(np.float32)
-        if (inside && k == 0 && (unsigned)(r - 1) < (unsigned)(TILE + 2) && (unsigned)(c - 1) < (unsigned)(TILE + 2))
+        if (inside && key == 0 && (unsigned)(r - 1) < (unsigned)(TH + 2) && (unsigned)(c - 1) < (unsigned)(TW + 2))
             s_hole_pos[atomicAdd(&s_nholes, 1)] = (unsigned short)pos;
     }
     __syncthreads();
 
-    // 2. hole fill: NaN cell <- median of its non-NaN 3x3 neighbours in the PRE-fill grid (dense over the list;
-    //    results are staged so that the fill does not cascade, lib/proj_to_grid.py:65)
+    // 2. hole fill: NaN cell <- median of its non-NaN 3x3 neighbours in the PRE-fill grid, dense over the list.
+    //    The fill must not cascade (lib/proj_to_grid.py:65 reads a copy): with one shared tile the results are
+    //    staged and patched in after a barrier; the float64 path reads s_raw and writes the separate float32 tile.
     const int nholes = s_nholes;
-    for (int h = tid; h < nholes; h += kThreads) {
-        const T* c = s_raw + s_hole_pos[h];
-        T nb[8] = {c[-TS - 1], c[-TS], c[-TS + 1], c[-1], c[1], c[TS - 1], c[TS], c[TS + 1]};
-        const T v = vs_median_of_valid8<T>(nb);
-        s_hole_val[h] = v;
-        if (v != v) s_has_nan = 1;
+    if (nholes > 0) {   // block-uniform
+        for (int h = tid; h < nholes; h += kThreads) {
+            const int pos = s_hole_pos[h];
+            const T* c = s_raw + pos;
+            T nb[8] = {c[-TS - 1], c[-TS], c[-TS + 1], c[-1], c[1], c[TS - 1], c[TS], c[TS + 1]};
+            const T v = vs_median_of_valid8<T>(nb);
+            if (v != v) s_has_nan = 1;
+            if (kSameTile) {
+                s_hole_val[h] = (float)v;
+            } else {
+                s_fill[pos] = (float)v;
+                if (filled_out != nullptr) {
+                    const int r = pos / TS, cc = pos - r * TS - OFF;
+                    const int gy = ty0 - 2 + r, gx = tx0 - 2 + cc;
+                    if (r >= 2 && r < TH + 2 && cc >= 2 && cc < TW + 2) filled_out[(size_t)gy * W + gx] = v;
+                }
+            }
+        }
+        __syncthreads();
+        if (kSameTile) {
+            for (int h = tid; h < nholes; h += kThreads) s_fill[s_hole_pos[h]] = s_hole_val[h];
+            __syncthreads();
+        }
     }
-    __syncthreads();
-    for (int h = tid; h < nholes; h += kThreads) {
-        const int pos = s_hole_pos[h];
-        const T v = s_hole_val[h];
-        s_raw[pos] = v;
-        if (!kSameTile) s_fill[pos] = (float)v;
-    }
-    __syncthreads();
     if (filled_out != nullptr) {
-#pragma unroll
-        for (int k = 0; k < TILE / 8; ++k) {
-            const int r = ty + 8 * k, gy = ty0 + r, gx = tx0 + tx;
-            if (gy < H && gx < W) filled_out[(size_t)gy * W + gx] = s_raw[(r + 2) * TS + (tx + 2)];
+        for (int i = tid; i < TW * TH; i += kThreads) {
+            const int r = i / TW, c = i - r * TW;
+            const int gy = ty0 + r, gx = tx0 + c;
+            const T v = s_raw[(r + 2) * TS + OFF + c + 2];
+            if (gy < H && gx < W && (kSameTile || v == v)) filled_out[(size_t)gy * W + gx] = v;
         }
     }
     if (blur_out == nullptr) return;
@@ -205,35 +260,26 @@ k_grid_finalize(const Key* __restrict__ keygrid, int W, int H, typename KeyTrait
 __global__ void __launch_bounds__(kThreads)
 k_median3x3(const float* __restrict__ in, int in_row0, int H, int W, int row_begin, int row_end,
             float* __restrict__ out, int simd_cols, unsigned long long* __restrict__ nan_count) {
-    __shared__ float s_fill[TR * TS];
+    __shared__ __align__(16) float s_fill[TR * TS];
     __shared__ int s_has_nan;
-    const int tx = threadIdx.x, ty = threadIdx.y;
-    const int tx0 = blockIdx.x * TILE, ty0 = row_begin + blockIdx.y * TILE;
-    if (ty == 0 && tx == 0) s_has_nan = 0;
+    const int tid = threadIdx.x;
+    const int tx0 = blockIdx.x * TW, ty0 = row_begin + blockIdx.y * TH;
+    if (tid == 0) s_has_nan = 0;
     __syncthreads();
     bool saw_nan = false;
-#pragma unroll
-    for (int it = 0; it < (TR + 7) / 8; ++it) {
-        const int r = ty + 8 * it;
-        if (r >= 1 && r <= TILE + 2) {
-            const int gy = ty0 - 2 + r;
-            // rows the caller supplies: max(row_begin-1, 0) .. min(row_end, H-1)
-            const bool row_ok = gy >= 0 && gy < H && gy >= row_begin - 1 && gy <= row_end;
-            const float* __restrict__ row = in + (size_t)(row_ok ? gy - in_row0 : 0) * W;
-#pragma unroll
-            for (int pass = 0; pass < 2; ++pass) {
-                const int c = pass * 32 + tx;
-                if (pass == 0 || tx < 4) {
-                    const int gx = tx0 - 2 + c;
-                    const bool inside = row_ok && gx >= 0 && gx < W;
-                    const float v = inside ? row[gx] : CUDART_NAN_F;
-                    s_fill[r * TS + c] = v;
-                    saw_nan |= inside && (v != v) && c >= 1 && c <= TILE + 2;
-                }
-            }
+    for (int i = tid; i < (TH + 2) * (TW + 2); i += kThreads) {
+        const int r = 1 + i / (TW + 2), c = 1 + i % (TW + 2);
+        const int gy = ty0 - 2 + r, gx = tx0 - 2 + c;
+        // rows the caller supplies: max(row_begin-1, 0) .. min(row_end, H-1)
+        const bool inside = (unsigned)gy < (unsigned)H && gy >= row_begin - 1 && gy <= row_end && (unsigned)gx < (unsigned)W;
+        float v = CUDART_NAN_F;
+        if (inside) {
+            v = in[(size_t)(gy - in_row0) * W + gx];
+            saw_nan |= (v != v);
         }
+        s_fill[r * TS + OFF + c] = v;
     }
-    if (__any_sync(0xffffffffu, saw_nan) && tx == 0) s_has_nan = 1;
+    if (saw_nan) s_has_nan = 1;
     __syncthreads();
     replicate_border(s_fill, ty0, tx0, H, W);
     __syncthreads();
@@ -257,8 +303,8 @@ int vs_grid_finalize(vs_ctx* ctx, const uint32_t* keygrid, int32_t xsize, int32_
     if (!guard.ok) return vs_cuda_fail(cudaGetLastError(), "cudaSetDevice");
     cudaStream_t stream = (cudaStream_t)stream_;
     if (nan_count) VS_CUDA(cudaMemsetAsync(nan_count, 0, sizeof(uint64_t), stream));
-    dim3 grid((xsize + TILE - 1) / TILE, (ysize + TILE - 1) / TILE);
-    k_grid_finalize<uint32_t><<<grid, dim3(32, 8), 0, stream>>>(keygrid, xsize, ysize, nullptr, dsm_out,
+    dim3 grid((xsize + TW - 1) / TW, (ysize + TH - 1) / TH);
+    k_grid_finalize<uint32_t><<<grid, kThreads, 0, stream>>>(keygrid, xsize, ysize, nullptr, dsm_out,
                                                             simd_cols_for(xsize, simd_lanes),
                                                             reinterpret_cast<unsigned long long*>(nan_count));
     VS_CHECK_LAUNCH(ctx, "k_grid_finalize<u32>");
@@ -274,8 +320,8 @@ int vs_grid_finalize64(vs_ctx* ctx, const uint64_t* keygrid64, int32_t xsize, in
     VsDeviceGuard guard(ctx->device);
     if (!guard.ok) return vs_cuda_fail(cudaGetLastError(), "cudaSetDevice");
     cudaStream_t stream = (cudaStream_t)stream_;
-    dim3 grid((xsize + TILE - 1) / TILE, (ysize + TILE - 1) / TILE);
-    k_grid_finalize<unsigned long long><<<grid, dim3(32, 8), 0, stream>>>(
+    dim3 grid((xsize + TW - 1) / TW, (ysize + TH - 1) / TH);
+    k_grid_finalize<unsigned long long><<<grid, kThreads, 0, stream>>>(
         reinterpret_cast<const unsigned long long*>(keygrid64), xsize, ysize, filled64, blurred32,
         simd_cols_for(xsize, simd_lanes), nullptr);
     VS_CHECK_LAUNCH(ctx, "k_grid_finalize<u64>");
@@ -295,8 +341,8 @@ int vs_median3x3(vs_ctx* ctx, const float* in, int32_t in_row0, int32_t H_total,
     if (nan_count) VS_CUDA(cudaMemsetAsync(nan_count, 0, sizeof(uint64_t), stream));
     if (row_begin == row_end) return VS_OK;
     VS_REQUIRE(in != nullptr && out != nullptr, "vs_median3x3: NULL array");
-    dim3 grid((W + TILE - 1) / TILE, (row_end - row_begin + TILE - 1) / TILE);
-    k_median3x3<<<grid, dim3(32, 8), 0, stream>>>(in, in_row0, H_total, W, row_begin, row_end, out,
+    dim3 grid((W + TW - 1) / TW, (row_end - row_begin + TH - 1) / TH);
+    k_median3x3<<<grid, kThreads, 0, stream>>>(in, in_row0, H_total, W, row_begin, row_end, out,
                                                simd_cols_for(W, simd_lanes),
                                                reinterpret_cast<unsigned long long*>(nan_count));
     VS_CHECK_LAUNCH(ctx, "k_median3x3");

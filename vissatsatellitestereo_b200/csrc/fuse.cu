@@ -295,8 +295,11 @@ k_fuse_large(const float* __restrict__ views, int64_t plane_stride, int V, int64
 
     // 5. nanmean of the survivors in numpy's pairwise order: lane j < 8 owns accumulator r[j]
     const KeepFn y{views + cell, plane_stride, med, mad};
-    const int j = lane & 7;
-    const bool acc_lane = lane < 8;
+    // numpy's 8 strided accumulators r[0..7] are spread over the first AL = min(LANES, 8) lanes of the group:
+    // lane q < AL owns r[q], r[q + AL], ...
+    constexpr int AL = LANES < 8 ? LANES : 8;
+    constexpr int ACC = 8 / AL;
+    const bool acc_lane = lane < AL;
     int cnt = 0;
     float total = 0.0f;
     {
@@ -325,17 +328,25 @@ k_fuse_large(const float* __restrict__ views, int64_t plane_stride, int V, int64
                 leaf = 0.0f;
                 for (int i = 0; i < n; ++i) leaf = __fadd_rn(leaf, y(off + i));   // every lane computes the same value
             } else {
-                float r = 0.0f;
+                float r[ACC];
+#pragma unroll
+                for (int m = 0; m < ACC; ++m) r[m] = 0.0f;
                 const int nfull = n - (n & 7);
                 if (acc_lane) {
-                    r = y(off + j);
-                    for (int i = 8; i < nfull; i += 8) r = __fadd_rn(r, y(off + i + j));
+#pragma unroll
+                    for (int m = 0; m < ACC; ++m) r[m] = y(off + lane + m * AL);
+                    for (int i = 8; i < nfull; i += 8) {
+#pragma unroll
+                        for (int m = 0; m < ACC; ++m) r[m] = __fadd_rn(r[m], y(off + i + lane + m * AL));
+                    }
                 }
-                // ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) over lanes 0..7 of the group
-                float t = __fadd_rn(r, __shfl_xor_sync(gmask, r, 1));
-                t = __fadd_rn(t, __shfl_xor_sync(gmask, t, 2));
-                t = __fadd_rn(t, __shfl_xor_sync(gmask, t, 4));
-                leaf = __shfl_sync(gmask, t, 0, LANES);
+                // gather r[0..7] (accumulator a lives in lane a % AL, slot a / AL) and combine as numpy does:
+                // ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7))
+                float a8[8];
+#pragma unroll
+                for (int a = 0; a < 8; ++a) a8[a] = __shfl_sync(gmask, r[a / AL], a % AL, LANES);
+                leaf = __fadd_rn(__fadd_rn(__fadd_rn(a8[0], a8[1]), __fadd_rn(a8[2], a8[3])),
+                                 __fadd_rn(__fadd_rn(a8[4], a8[5]), __fadd_rn(a8[6], a8[7])));
                 for (int i = nfull; i < n; ++i) leaf = __fadd_rn(leaf, y(off + i));
             }
             // ---- combine with finished left siblings
@@ -384,7 +395,9 @@ int launch_large(vs_ctx* ctx, const float* views, int64_t plane_stride, int V, i
                  cudaStream_t stream) {
 #define VS_TRY(LANES, NVL) \
     if (V <= LANES * NVL) return launch_large_t<LANES, NVL>(ctx, views, plane_stride, V, n_cells, out, stream);
-    VS_TRY(8, 16) VS_TRY(8, 24) VS_TRY(8, 32) VS_TRY(8, 40) VS_TRY(8, 48) VS_TRY(8, 56) VS_TRY(8, 64)
+    VS_TRY(2, 40) VS_TRY(2, 48) VS_TRY(2, 56) VS_TRY(2, 64)
+    VS_TRY(4, 40) VS_TRY(4, 48) VS_TRY(4, 56) VS_TRY(4, 64)
+    VS_TRY(8, 40) VS_TRY(8, 48) VS_TRY(8, 56) VS_TRY(8, 64)
     VS_TRY(32, 24) VS_TRY(32, 32) VS_TRY(32, 48) VS_TRY(32, 64)
 #undef VS_TRY
     vs_set_error("vs_fuse_views: more than 2048 views");
