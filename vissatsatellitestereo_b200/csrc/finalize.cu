@@ -195,19 +195,61 @@ k_grid_finalize(const Key* __restrict__ keygrid, int W, int H, typename KeyTrait
     __syncthreads();
 
     // 1. decode keys (+2 halo).  Key 0 (= empty, also used outside the grid) decodes to NaN, and the fill only
-    //    uses in-range neighbours (:73).  Holes = empty cells inside the grid within the 1-cell halo.
-    for (int i = tid; i < TR * TC; i += kThreads) {
-        const int r = i / TC, c = i - r * TC;
-        const int gy = ty0 - 2 + r, gx = tx0 - 2 + c;
-        const bool inside = (unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W;
-        Key key = 0;
-        if (inside) key = keygrid[(size_t)gy * W + gx];
-        const T v = KeyTraits<Key>::decode(key);
-        const int pos = r * TS + OFF + c;
-        s_raw[pos] = v;
-        if (!kSameTile) s_fill[pos] = (float)v;     // produce_dsm.py:58 astype(np.float32)
-        if (inside && key == 0 && (unsigned)(r - 1) < (unsigned)(TH + 2) && (unsigned)(c - 1) < (unsigned)(TW + 2))
-            s_hole_pos[atomicAdd(&s_nholes, 1)] = (unsigned short)pos;
+    //    uses in-range neighbours (:73).  Holes = empty cells inside the grid within the 1-cell halo; they are
+    //    appended to a list with one shared atomic per warp-row (ballot-aggregated).
+    //    Warp w loads tile rows w, w+8, ...; lane l takes columns l, l+32 and (l < 4) l+64: no div/mod, and the
+    //    row address is computed once per row.
+    {
+        const int warp = tid >> 5, lane = tid & 31;
+        constexpr int NIT = (TR + 7) / 8;   // rows per warp
+        // 1a. issue every global load of this thread before touching the results (memory-level parallelism: the
+        //     phase is latency-bound otherwise)
+        Key keys[NIT][3];
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int r = warp + 8 * it;
+            const int gy = ty0 - 2 + r;
+            const bool row_ok = r < TR && (unsigned)gy < (unsigned)H;
+            const Key* __restrict__ row = keygrid + (size_t)(row_ok ? gy : 0) * W + (tx0 - 2);
+#pragma unroll
+            for (int part = 0; part < 3; ++part) {
+                const int c = lane + 32 * part;
+                const int gx = tx0 - 2 + c;
+                Key key = 0;
+                if (row_ok && (part < 2 || lane < TC - 64) && (unsigned)gx < (unsigned)W) key = row[c];
+                keys[it][part] = key;
+            }
+        }
+        // 1b. decode, store, list holes
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int r = warp + 8 * it;
+            if (r < TR) {   // warp-uniform
+                const int gy = ty0 - 2 + r;
+                const bool row_in = (unsigned)gy < (unsigned)H && (unsigned)(r - 1) < (unsigned)(TH + 2);
+#pragma unroll
+                for (int part = 0; part < 3; ++part) {
+                    const int c = lane + 32 * part;
+                    const int pos = r * TS + OFF + c;
+                    bool hole = false;
+                    if (part < 2 || lane < TC - 64) {
+                        const Key key = keys[it][part];
+                        const T v = KeyTraits<Key>::decode(key);
+                        s_raw[pos] = v;
+                        if (!kSameTile) s_fill[pos] = (float)v;     // produce_dsm.py:58 astype(np.float32)
+                        const int gx = tx0 - 2 + c;
+                        hole = key == 0 && row_in && (unsigned)gx < (unsigned)W && (unsigned)(c - 1) < (unsigned)(TW + 2);
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, hole);
+                    if (m) {   // warp-uniform
+                        int base = 0;
+                        if (lane == 0) base = atomicAdd(&s_nholes, __popc(m));
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                        if (hole) s_hole_pos[base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)pos;
+                    }
+                }
+            }
+        }
     }
     __syncthreads();
 
@@ -267,17 +309,45 @@ k_median3x3(const float* __restrict__ in, int in_row0, int H, int W, int row_beg
     if (tid == 0) s_has_nan = 0;
     __syncthreads();
     bool saw_nan = false;
-    for (int i = tid; i < (TH + 2) * (TW + 2); i += kThreads) {
-        const int r = 1 + i / (TW + 2), c = 1 + i % (TW + 2);
-        const int gy = ty0 - 2 + r, gx = tx0 - 2 + c;
-        // rows the caller supplies: max(row_begin-1, 0) .. min(row_end, H-1)
-        const bool inside = (unsigned)gy < (unsigned)H && gy >= row_begin - 1 && gy <= row_end && (unsigned)gx < (unsigned)W;
-        float v = CUDART_NAN_F;
-        if (inside) {
-            v = in[(size_t)(gy - in_row0) * W + gx];
-            saw_nan |= (v != v);
+    {
+        const int warp = tid >> 5, lane = tid & 31;
+        constexpr int NIT = (TH + 2 + 7) / 8;
+        float vals[NIT][3];
+        // issue every global load first (memory-level parallelism), then store to shared memory
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int r = 1 + warp + 8 * it;
+            const int gy = ty0 - 2 + r;
+            // rows the caller supplies: max(row_begin-1, 0) .. min(row_end, H-1)
+            const bool row_ok = r < TH + 3 && (unsigned)gy < (unsigned)H && gy >= row_begin - 1 && gy <= row_end;
+            const float* __restrict__ row = in + (size_t)(row_ok ? gy - in_row0 : 0) * W + (tx0 - 2);
+#pragma unroll
+            for (int part = 0; part < 3; ++part) {
+                const int c = 1 + lane + 32 * part;
+                const int gx = tx0 - 2 + c;
+                float v = CUDART_NAN_F;
+                if (row_ok && (part < 2 || lane < TW + 2 - 64) && (unsigned)gx < (unsigned)W) v = row[c];
+                vals[it][part] = v;
+            }
         }
-        s_fill[r * TS + OFF + c] = v;
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int r = 1 + warp + 8 * it;
+            if (r < TH + 3) {
+#pragma unroll
+                for (int part = 0; part < 3; ++part) {
+                    const int c = 1 + lane + 32 * part;
+                    if (part < 2 || lane < TW + 2 - 64) {
+                        const float v = vals[it][part];
+                        const int gy = ty0 - 2 + r, gx = tx0 - 2 + c;
+                        const bool inside = (unsigned)gy < (unsigned)H && gy >= row_begin - 1 && gy <= row_end &&
+                                            (unsigned)gx < (unsigned)W;
+                        saw_nan |= inside && (v != v);
+                        s_fill[r * TS + OFF + c] = v;
+                    }
+                }
+            }
+        }
     }
     if (saw_nan) s_has_nan = 1;
     __syncthreads();
