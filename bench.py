@@ -220,20 +220,17 @@ def run_b200_arm(args, cfg):
     stage_events = []
     exch_events = []
 
+    n_waves = 5 if world > 1 else 1
+    wave_edges = [round(i * V / n_waves) for i in range(n_waves + 1)]
+
+    xch = D.WaveExchanger(stack, view_counts) if (world > 1 and cfg.fuse) else None     # buffers allocated once
+
     def step(record):
-        evs = []
-        for v in range(V):
-            eng.clear_keygrid()
-            if record:
-                a, b, c = ev(), ev(), ev()
-                a.record()
-            eng.rasterize(depths[v], mats[v], clear=False)
-            if record:
-                b.record()
-            eng.finalize(out=stack[v])
-            if record:
-                c.record()
-                evs.append((a, b, c))
+        for w in range(n_waves):
+            a, b = wave_edges[w], wave_edges[w + 1]
+            eng.views_to_dsm(depths[a:b], mats[a:b], stack, first=a)     # one library call per wave (stages A + B)
+            if xch is not None:
+                xch.send_wave(a, b)                                      # overlaps stages A/B of the next wave
         fe = None
         if cfg.fuse:
             if record:
@@ -247,7 +244,7 @@ def run_b200_arm(args, cfg):
             else:
                 if record:
                     x0 = ev()
-                band_stack, (r0, r1), (h0, h1) = D.exchange_rowbands(stack, view_counts, eng.n_size)
+                band_stack, (r0, r1), (h0, h1) = xch.finish()       # waits only for what is still in flight
                 if record:
                     x0.record()
                 mean = eng.fuse(band_stack)
@@ -262,7 +259,7 @@ def run_b200_arm(args, cfg):
         else:
             fused = None
         if record:
-            stage_events.append((evs, fe))
+            stage_events.append(fe)
         return fused
 
     def barrier():
@@ -277,6 +274,7 @@ def run_b200_arm(args, cfg):
     if rank == 0:
         sampler.start()
     launches0 = eng.launch_count()
+    eng.set_timing(True)           # CUDA events around stage A / stage B of every view, recorded inside the library
     t0, t1 = ev(), ev()
     barrier()
     t0.record()
@@ -295,10 +293,10 @@ def run_b200_arm(args, cfg):
     value = mpix_step / (ms_step * 1e-3)
 
     # per-stage device times inside the timed region
-    k1 = np.array([a.elapsed_time(b) for evs, _ in stage_events for (a, b, c) in evs])
-    k2 = np.array([b.elapsed_time(c) for evs, _ in stage_events for (a, b, c) in evs])
-    fuse_ms = np.array([fe[0].elapsed_time(fe[1]) for _, fe in stage_events if fe]) if cfg.fuse else np.array([0.0])
-    blur_ms = np.array([fe[1].elapsed_time(fe[2]) for _, fe in stage_events if fe]) if cfg.fuse else np.array([0.0])
+    k1, k2 = eng.get_timing()
+    eng.set_timing(False)
+    fuse_ms = np.array([fe[0].elapsed_time(fe[1]) for fe in stage_events if fe]) if cfg.fuse else np.array([0.0])
+    blur_ms = np.array([fe[1].elapsed_time(fe[2]) for fe in stage_events if fe]) if cfg.fuse else np.array([0.0])
     exch_ms = np.array([a.elapsed_time(b) for a, b in exch_events]) if exch_events else np.array([0.0])
     stages = {'k1_unproject_scatter_ms_per_view': float(k1.mean()), 'k2_grid_finalize_ms_per_view': float(k2.mean()),
               'k3_fuse_ms_per_step' if world == 1 else 'exchange_plus_fuse_ms_per_step': float(fuse_ms.mean()),

@@ -134,6 +134,27 @@ int vs_grid_finalize(vs_ctx* ctx, const uint32_t* keygrid, int32_t xsize, int32_
 int vs_grid_finalize64(vs_ctx* ctx, const uint64_t* keygrid64, int32_t xsize, int32_t ysize, double* filled64,
                        float* blurred32, int simd_lanes, void* stream);
 
+/* ---- stages A + B for a batch of views in one call -------------------------------------------------------------
+ * aggregate_2p5d_util.convert_depth_maps' loop body (:138-146 -> :75-102) for n_views views: for each view clear the
+ * key grid, vs_unproject_rasterize, vs_grid_finalize into plane v of dsm_stack.  Same kernels as the single-view
+ * entry points; exists so that a host language with expensive FFI calls (Python/ctypes) issues one call per batch.
+ *   depth        host array of n_views device pointers (float32 H[v]*W[v] each)
+ *   H, W         host arrays of n_views image sizes
+ *   inv_proj_mats host n_views*16 doubles
+ *   dsm_stack    dev float32; plane v at dsm_stack + v*plane_stride, ysize*xsize each
+ *   nan_counts   dev uint64[n_views] or NULL (empty cells per view, aggregate_2p5d.py:63)
+ *   stats        dev uint64[n_views*VS_NUM_STATS] or NULL
+ */
+int vs_views_to_dsm(vs_ctx* ctx, int32_t n_views, const float* const* depth, const int32_t* H, const int32_t* W,
+                    const double* inv_proj_mats, uint32_t* keygrid, float* dsm_stack, int64_t plane_stride,
+                    int simd_lanes, uint64_t* nan_counts, uint64_t* stats, void* stream);
+
+/* Per-kernel device timing of vs_views_to_dsm (CUDA events recorded on the launching stream around stage A and stage
+ * B of every view).  vs_set_timing(ctx, 1) enables it and resets the log; vs_get_timing synchronises the events and
+ * returns up to `max` (stage A ms, stage B ms) pairs in call order; *n_out = number of views logged. */
+int vs_set_timing(vs_ctx* ctx, int enable);
+int vs_get_timing(vs_ctx* ctx, int32_t max, float* stage_a_ms, float* stage_b_ms, int32_t* n_out);
+
 /* ---- stage C: cross-view fusion --------------------------------------------------------------------------
  * Replaces aggregate_2p5d.py:65-78: per cell over V views (in the given order = sorted file order):
  * count filter (<= 2 measurements -> NaN), np.nanmedian, MAD = nanmedian(|x - med|), reject |x - med| > MAD,

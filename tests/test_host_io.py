@@ -90,6 +90,13 @@ def _exchange_worker(rank, world, port, n_rows, W, counts, out):
         band_stack, (r0, r1), (h0, h1) = D.exchange_rowbands(local, counts, n_rows)
         want = torch.stack([rows[h0:h1] + v * 1e6 for v in range(sum(counts))])
         ok = torch.equal(band_stack, want)
+        # the wave form (what the benchmark overlaps with compute) must deliver the same stack
+        xch = D.WaveExchanger(local, counts)
+        vmax = max(counts)
+        for a in range(0, vmax, 2):
+            xch.send_wave(a, min(a + 2, vmax))
+        bs2, band2, halo2 = xch.finish()
+        ok = ok and torch.equal(bs2, want) and band2 == (r0, r1) and halo2 == (h0, h1)
         # a fake "fusion" (mean over views of the band) and the gather of the bands on rank 0
         band = band_stack.mean(dim=0)[r0 - h0: r1 - h0].contiguous()
         full = D.gather_bands(band, n_rows, W)

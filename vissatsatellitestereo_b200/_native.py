@@ -53,6 +53,10 @@ SIGNATURES = {
     'vs_points_rasterize': (C.c_int, [_vp, _vp, _i64, _dbl, _dbl, _dbl, _dbl, _i32, _i32, _vp, C.c_int, _vp, _vp]),
     'vs_grid_finalize': (C.c_int, [_vp, _vp, _i32, _i32, _vp, C.c_int, _vp, _vp]),
     'vs_grid_finalize64': (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, C.c_int, _vp]),
+    'vs_views_to_dsm': (C.c_int, [_vp, _i32, C.POINTER(_vp), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_dbl), _vp, _vp,
+                                  _i64, C.c_int, _vp, _vp, _vp]),
+    'vs_set_timing': (C.c_int, [_vp, C.c_int]),
+    'vs_get_timing': (C.c_int, [_vp, _i32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(_i32)]),
     'vs_fuse_views': (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),
     'vs_median3x3': (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, C.c_int, _vp, _vp]),
     'vs_enu_to_geodetic': (C.c_int, [_vp, _vp, _vp, _vp, _i64, _dbl, _dbl, _dbl, _vp, _vp, _vp, _vp]),

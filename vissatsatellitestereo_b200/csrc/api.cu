@@ -134,6 +134,8 @@ int vs_ctx_create(int device, vs_ctx** out) {
     ctx->d_scratch = nullptr;
     ctx->scratch_doubles = 0;
     ctx->d_exact = nullptr;
+    ctx->timing = false;
+    ctx->ev_used = 0;
     *out = ctx;
     return VS_OK;
 }
@@ -143,6 +145,7 @@ int vs_ctx_destroy(vs_ctx* ctx) {
     VsDeviceGuard guard(ctx->device);
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     if (ctx->d_exact) cudaFree(ctx->d_exact);
+    for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     delete ctx;
     return VS_OK;
 }

@@ -1,0 +1,70 @@
+// Batched stage A + B: one C call for many views (the host language pays one FFI crossing per batch).
+#include "vs_common.cuh"
+
+extern "C" {
+
+int vs_views_to_dsm(vs_ctx* ctx, int32_t n_views, const float* const* depth, const int32_t* H, const int32_t* W,
+                    const double* inv_proj_mats, uint32_t* keygrid, float* dsm_stack, int64_t plane_stride,
+                    int simd_lanes, uint64_t* nan_counts, uint64_t* stats, void* stream_) {
+    VS_REQUIRE(ctx != nullptr, "vs_views_to_dsm: NULL context");
+    if (!ctx->aoi_set) {
+        vs_set_error("vs_views_to_dsm: call vs_set_aoi first");
+        return VS_ERR_STATE;
+    }
+    VS_REQUIRE(n_views >= 0, "vs_views_to_dsm: negative view count");
+    if (n_views == 0) return VS_OK;
+    VS_REQUIRE(depth && H && W && inv_proj_mats && keygrid && dsm_stack, "vs_views_to_dsm: NULL argument");
+    const int xs = ctx->aoi.xsize, ys = ctx->aoi.ysize;
+    VS_REQUIRE(plane_stride >= (int64_t)xs * ys, "vs_views_to_dsm: plane_stride smaller than a plane");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    VsDeviceGuard guard(ctx->device);
+    if (!guard.ok) return vs_cuda_fail(cudaGetLastError(), "cudaSetDevice");
+    if (ctx->timing) {
+        const size_t need = ctx->ev_used + 3 * (size_t)n_views;
+        while (ctx->ev_pool.size() < need) {
+            cudaEvent_t e;
+            VS_CUDA(cudaEventCreate(&e));
+            ctx->ev_pool.push_back(e);
+        }
+    }
+    for (int v = 0; v < n_views; ++v) {
+        int rc = vs_keygrid_clear(ctx, keygrid, (int64_t)xs * ys, 4, stream_);
+        if (rc) return rc;
+        if (ctx->timing) VS_CUDA(cudaEventRecord(ctx->ev_pool[ctx->ev_used + 0], stream));
+        rc = vs_unproject_rasterize(ctx, depth[v], H[v], W[v], inv_proj_mats + 16 * (size_t)v, keygrid, 0, nullptr,
+                                    stats ? stats + (size_t)v * VS_NUM_STATS : nullptr, stream_);
+        if (rc) return rc;
+        if (ctx->timing) VS_CUDA(cudaEventRecord(ctx->ev_pool[ctx->ev_used + 1], stream));
+        rc = vs_grid_finalize(ctx, keygrid, xs, ys, dsm_stack + (size_t)v * plane_stride, simd_lanes,
+                              nan_counts ? nan_counts + v : nullptr, stream_);
+        if (rc) return rc;
+        if (ctx->timing) {
+            VS_CUDA(cudaEventRecord(ctx->ev_pool[ctx->ev_used + 2], stream));
+            ctx->ev_used += 3;
+        }
+    }
+    return VS_OK;
+}
+
+int vs_set_timing(vs_ctx* ctx, int enable) {
+    VS_REQUIRE(ctx != nullptr, "vs_set_timing: NULL context");
+    ctx->timing = enable != 0;
+    ctx->ev_used = 0;
+    return VS_OK;
+}
+
+int vs_get_timing(vs_ctx* ctx, int32_t max, float* stage_a_ms, float* stage_b_ms, int32_t* n_out) {
+    VS_REQUIRE(ctx != nullptr && n_out != nullptr, "vs_get_timing: NULL argument");
+    VsDeviceGuard guard(ctx->device);
+    if (!guard.ok) return vs_cuda_fail(cudaGetLastError(), "cudaSetDevice");
+    const int n = (int)(ctx->ev_used / 3);
+    *n_out = n;
+    for (int i = 0; i < n && i < max; ++i) {
+        VS_CUDA(cudaEventSynchronize(ctx->ev_pool[3 * i + 2]));
+        if (stage_a_ms) VS_CUDA(cudaEventElapsedTime(stage_a_ms + i, ctx->ev_pool[3 * i], ctx->ev_pool[3 * i + 1]));
+        if (stage_b_ms) VS_CUDA(cudaEventElapsedTime(stage_b_ms + i, ctx->ev_pool[3 * i + 1], ctx->ev_pool[3 * i + 2]));
+    }
+    return VS_OK;
+}
+
+}  // extern "C"

@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <vector>
 
 #include "../../include/vissat_b200.h"
 
@@ -53,6 +54,10 @@ struct vs_ctx {
     double* d_scratch;
     size_t scratch_doubles;
     void* d_exact;  // VsExactParams on the device (geo_chain.cuh)
+    // optional per-view kernel timing of vs_views_to_dsm
+    bool timing;
+    std::vector<cudaEvent_t> ev_pool;   // 3 events per logged view: before A, between A and B, after B
+    size_t ev_used;
 };
 
 void vs_set_error(const std::string& msg);

@@ -63,6 +63,89 @@ def exchange_rowbands(local_stack, view_counts, n_rows, group=None, halo=1):
     return recv.view(v_total, my_rows, W), bands[rank], (h0, h1)
 
 
+class WaveExchanger:
+    """The same all-to-all, issued in waves on a side stream so that it overlaps stages A/B of later views.
+
+    Rank r calls `send_wave(a, b)` once views [a, b) of its local stack are final on the current stream; the wave is
+    packed and exchanged on `self.stream`.  `finish()` makes the current stream wait for every wave and returns the
+    (V_total, rows_with_halo, W) stack of this rank's row band, in global (sorted) view order.
+    """
+
+    def __init__(self, local_stack, view_counts, group=None, halo=1):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.local = local_stack
+        self.view_counts = list(view_counts)
+        self.n_rows, self.W = local_stack.shape[1], local_stack.shape[2]
+        self.bands = row_bands(self.n_rows, self.world)
+        self.bands_h = [band_with_halo(b, self.n_rows, halo) for b in self.bands]
+        self.h0, self.h1 = self.bands_h[self.rank]
+        self.first = [sum(self.view_counts[:i]) for i in range(self.world)]
+        v_total = sum(self.view_counts)
+        self.band_stack = torch.empty((v_total, self.h1 - self.h0, self.W), dtype=local_stack.dtype,
+                                      device=local_stack.device)
+        self.stream = torch.cuda.Stream(device=local_stack.device) if local_stack.is_cuda else None
+        # persistent pack buffers, one per destination rank: [view][band rows + halo][W].  Allocated once: the object
+        # is reused for every pass over the data (a fresh allocation per pass on a side stream would fall through the
+        # caching allocator to cudaMalloc and synchronise the device).
+        self.send_bufs = [torch.empty((local_stack.shape[0], h1 - h0, self.W), dtype=local_stack.dtype,
+                                      device=local_stack.device) for (h0, h1) in self.bands_h]
+        self._reqs = []
+
+    def send_wave(self, a, b):
+        """Exchange local views [a, b).  Every rank must call this with the same sequence of (a, b) (view counts are
+        equal per rank in the benchmark; ranks with fewer views pass empty ranges clipped to their count)."""
+        ranges = [(min(a, c), min(b, c)) for c in self.view_counts]      # views [a, b) of every source rank
+        la, lb = ranges[self.rank]
+        cur = torch.cuda.current_stream(self.local.device) if self.stream is not None else None
+        ctx = torch.cuda.stream(self.stream) if self.stream is not None else _NullCtx()
+        if self.stream is not None:
+            self.stream.wait_stream(cur)
+        with ctx:
+            send = []
+            for buf, (h0, h1) in zip(self.send_bufs, self.bands_h):
+                buf[la:lb].copy_(self.local[la:lb, h0:h1, :])          # pack (strided -> contiguous)
+                send.append(buf[la:lb])
+            recv = [self.band_stack[self.first[i] + ra: self.first[i] + rb] for i, (ra, rb) in enumerate(ranges)]
+            # own band: local copy (all_to_all on NCCL rewrites it with the same data); peers: grouped send/recv
+            if recv[self.rank].numel():
+                recv[self.rank].copy_(send[self.rank])
+            ops = []
+            if self.world > 1 and self.local.is_cuda:
+                # NCCL: the list form of all_to_all is one grouped ncclSend/ncclRecv batch on the main communicator
+                dist.all_to_all(recv, send, group=self.group)
+            elif self.world > 1:
+                # gloo (CPU tests) has no list all_to_all: batched isend/irecv
+                for peer in range(self.world):
+                    if peer == self.rank:
+                        continue
+                    if send[peer].numel():
+                        ops.append(dist.P2POp(dist.isend, send[peer], peer, group=self.group))
+                    if recv[peer].numel():
+                        ops.append(dist.P2POp(dist.irecv, recv[peer], peer, group=self.group))
+            if ops:
+                self._reqs.extend(dist.batch_isend_irecv(ops))
+
+    def finish(self):
+        ctx = torch.cuda.stream(self.stream) if self.stream is not None else _NullCtx()
+        with ctx:
+            for q in self._reqs:
+                q.wait()             # on NCCL: stream-level wait on the side stream; on gloo: host wait
+        if self.stream is not None:
+            torch.cuda.current_stream(self.local.device).wait_stream(self.stream)
+        self._reqs = []
+        return self.band_stack, self.bands[self.rank], (self.h0, self.h1)
+
+
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
 def fuse_distributed(engine, local_stack, view_counts, group=None):
     """Stage C across ranks: exchange, fuse own row band, blur it.  Returns (band float32 (rows, W), (r0, r1))."""
     n_rows = local_stack.shape[1]

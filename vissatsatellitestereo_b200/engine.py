@@ -109,6 +109,33 @@ class DsmEngine:
         self.rasterize(depth, inv_proj_mat, height_map=height_map)
         return self.finalize(out=out)
 
+    def views_to_dsm(self, depths, mats, stack, first=0, count_nan=None):
+        """Stages A + B for a batch of views in ONE library call (vs_views_to_dsm): view i of `depths` -> stack[first + i].
+        depths: list of (H, W) float32 device tensors; mats: list of 4x4."""
+        n = len(depths)
+        if n == 0:
+            return
+        ptrs = (C.c_void_p * n)(*[d.data_ptr() for d in depths])
+        Hs = (C.c_int32 * n)(*[d.shape[0] for d in depths])
+        Ws = (C.c_int32 * n)(*[d.shape[1] for d in depths])
+        M = np.ascontiguousarray(np.stack([np.asarray(m, dtype=np.float64).reshape(16) for m in mats]))
+        out = stack[first:first + n]
+        assert out.is_contiguous() and out.dtype == torch.float32 and tuple(out.shape[1:]) == (self.n_size, self.e_size)
+        check(lib.vs_views_to_dsm(self.ctx.handle, n, ptrs, Hs, Ws, M.ctypes.data_as(C.POINTER(C.c_double)),
+                                  _ptr(self.keygrid), _ptr(out), stack.stride(0), self.simd_lanes,
+                                  _ptr(count_nan), C.c_void_p(0), _stream(self.device)), 'vs_views_to_dsm')
+
+    def set_timing(self, enable):
+        check(lib.vs_set_timing(self.ctx.handle, 1 if enable else 0), 'vs_set_timing')
+
+    def get_timing(self, max_views=65536):
+        a = (C.c_float * max_views)()
+        b = (C.c_float * max_views)()
+        n = C.c_int32(0)
+        check(lib.vs_get_timing(self.ctx.handle, max_views, a, b, C.byref(n)), 'vs_get_timing')
+        k = min(n.value, max_views)
+        return np.array(a[:k], dtype=np.float64), np.array(b[:k], dtype=np.float64)
+
     def stats(self):
         """Counters of the last rasterize call (synchronises)."""
         s = self._stats.cpu().numpy()
