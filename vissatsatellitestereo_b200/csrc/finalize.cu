@@ -12,167 +12,11 @@
 //       * a tile without any NaN left skips every NaN test; otherwise each window with a NaN goes through the
 //         exact emulation of OpenCV's 19-exchange network (SIMD / scalar column semantics).
 // K4  k_median3x3            aggregate_2p5d.py:81 on a row band (halo rows supplied by the caller); same blur.
-#include <math_constants.h>
+#include "finalize_common.cuh"
 
-#include "median.cuh"
-#include "vs_common.cuh"
+using namespace vsfin;
 
 namespace {
-
-constexpr int TW = 64;            // tile width  (outputs)
-constexpr int TH = 32;            // tile height (outputs)
-constexpr int kThreads = 256;
-constexpr int OFF = 3;            // column offset of the tile inside a shared row: makes the 6-float window of a
-                                  // 4-wide patch start on a 16-byte boundary
-constexpr int TS = 72;            // shared row stride in elements (>= OFF + TW + 4, multiple of 4)
-constexpr int TR = TH + 4;        // shared rows (halo 2)
-constexpr int TC = TW + 4;        // shared columns in use (halo 2)
-constexpr int MAX_HOLES = (TH + 2) * (TW + 2);
-
-template <typename Key> struct KeyTraits;
-template <> struct KeyTraits<uint32_t> {
-    typedef float value_t;
-    static __device__ __forceinline__ float decode(uint32_t k) { return vs_unkey32(k); }
-};
-template <> struct KeyTraits<unsigned long long> {
-    typedef double value_t;
-    static __device__ __forceinline__ double decode(unsigned long long k) { return vs_unkey64(k); }
-};
-
-__device__ __forceinline__ void block_count_flush(unsigned local, unsigned long long* counter) {
-    if (counter == nullptr) return;
-    __shared__ unsigned s_cnt;
-    const int tid = threadIdx.x;
-    if (tid == 0) s_cnt = 0;
-    __syncthreads();
-    unsigned r = __reduce_add_sync(0xffffffffu, local);
-    if ((tid & 31) == 0 && r) atomicAdd(&s_cnt, r);
-    __syncthreads();
-    if (tid == 0 && s_cnt) atomicAdd(counter, (unsigned long long)s_cnt);
-}
-
-// ---- 3x3 median pieces ----------------------------------------------------------------------------------------
-struct Col3 {
-    float lo, mid, hi;
-};
-__device__ __forceinline__ Col3 sort_col3(float a, float b, float c) {
-    Col3 r;
-    const float ab_lo = fminf(a, b), ab_hi = fmaxf(a, b);
-    r.lo = fminf(ab_lo, c);
-    r.hi = fmaxf(ab_hi, c);
-    r.mid = fmaxf(ab_lo, fminf(ab_hi, c));
-    return r;
-}
-__device__ __forceinline__ float med3f(float a, float b, float c) {
-    return fmaxf(fminf(a, b), fminf(fmaxf(a, b), c));
-}
-// median of 9 from three sorted columns: med3(max of minima, med3 of medians, min of maxima)
-__device__ __forceinline__ float median_of_cols(const Col3& a, const Col3& b, const Col3& c) {
-    return med3f(fmaxf(fmaxf(a.lo, b.lo), c.lo), med3f(a.mid, b.mid, c.mid), fminf(fminf(a.hi, b.hi), c.hi));
-}
-__device__ __forceinline__ bool has_nan9(const float (&r0)[3], const float (&r1)[3], const float (&r2)[3]) {
-    const float sum = ((r0[0] + r0[1]) + (r0[2] + r1[0])) + ((r1[1] + r1[2]) + (r2[0] + r2[1])) + r2[2];
-    return !(sum == sum);   // NaN (or +inf with -inf): take the exact path
-}
-__device__ __forceinline__ float median9_exact(const float* r0, const float* r1, const float* r2, bool simd) {
-    return simd ? vs_median9_net<true>(r0[0], r0[1], r0[2], r1[0], r1[1], r1[2], r2[0], r2[1], r2[2])
-                : vs_median9_net<false>(r0[0], r0[1], r0[2], r1[0], r1[1], r1[2], r2[0], r2[1], r2[2]);
-}
-
-// Blur phase shared by K2 and K4.  s_fill: TR x TS tile; element (r, OFF + c) is grid cell (ty0 - 2 + r, tx0 - 2 + c).
-// Rows/columns within the 1-cell halo must be final (hole-filled) and, outside the grid, replicated from the
-// nearest inside cell.  Writes out[(gy - out_row0) * W + gx] for gy in [ty0, min(ty0 + TH, row_limit)).
-__device__ __forceinline__ unsigned blur_tile(const float* __restrict__ s_fill, int ty0, int tx0, int H, int W,
-                                              int row_limit, bool tile_has_nan, bool simd_cols,
-                                              float* __restrict__ out, int out_row0) {
-    const int tid = threadIdx.x;
-    unsigned n_nan = 0;
-    if (H == 1 || W == 1) {  // OpenCV's 1-D special case (block-uniform): 3-tap median along the line
-        for (int i = tid; i < TW * TH; i += kThreads) {
-            const int r = i / TW, c = i - r * TW;
-            const int gy = ty0 + r, gx = tx0 + c;
-            if (gy < row_limit && gx < W) {
-                const float* p = s_fill + (r + 2) * TS + (OFF + c + 2);
-                const float m = (H == 1) ? vs_median3_line(p[-1], p[0], p[1]) : vs_median3_line(p[-TS], p[0], p[TS]);
-                out[(size_t)(gy - out_row0) * W + gx] = m;
-                n_nan += (m != m);
-            }
-        }
-        return n_nan;
-    }
-    // patch of 4 columns x 2 rows per thread
-    const int k = tid & 15, rp = tid >> 4;          // strip 0..15, row pair 0..15
-    const int r = 2 * rp, c = 4 * k;
-    const int gy = ty0 + r, gx = tx0 + c;
-    if (gy >= row_limit || gx >= W) return 0;
-    // rows r-1 .. r+2 of the tile, columns c-1 .. c+4  ->  shared rows r+1 .. r+4, columns OFF+c+1 .. OFF+c+6
-    float win[4][6];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const float* p = s_fill + (r + 1 + j) * TS + (OFF + c + 1);   // 16-byte aligned
-        const float4 a = *reinterpret_cast<const float4*>(p);
-        const float2 b = *reinterpret_cast<const float2*>(p + 4);
-        win[j][0] = a.x; win[j][1] = a.y; win[j][2] = a.z; win[j][3] = a.w; win[j][4] = b.x; win[j][5] = b.y;
-    }
-    float res[2][4];
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        Col3 col[6];
-#pragma unroll
-        for (int x = 0; x < 6; ++x) col[x] = sort_col3(win[j][x], win[j + 1][x], win[j + 2][x]);
-#pragma unroll
-        for (int x = 0; x < 4; ++x) res[j][x] = median_of_cols(col[x], col[x + 1], col[x + 2]);
-    }
-    if (tile_has_nan) {  // block-uniform; rare
-#pragma unroll
-        for (int j = 0; j < 2; ++j)
-#pragma unroll
-            for (int x = 0; x < 4; ++x) {
-                const float r0[3] = {win[j][x], win[j][x + 1], win[j][x + 2]};
-                const float r1[3] = {win[j + 1][x], win[j + 1][x + 1], win[j + 1][x + 2]};
-                const float r2[3] = {win[j + 2][x], win[j + 2][x + 1], win[j + 2][x + 2]};
-                if (has_nan9(r0, r1, r2)) {
-                    const int x_g = gx + x;
-                    res[j][x] = median9_exact(r0, r1, r2, simd_cols && x_g >= 1 && x_g <= W - 2);
-                }
-            }
-    }
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        const int y_g = gy + j;
-        if (y_g < row_limit) {
-            float* o = out + (size_t)(y_g - out_row0) * W + gx;
-            if (gx + 3 < W && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-                *reinterpret_cast<float4*>(o) = make_float4(res[j][0], res[j][1], res[j][2], res[j][3]);
-#pragma unroll
-                for (int x = 0; x < 4; ++x) n_nan += (res[j][x] != res[j][x]);
-            } else {
-#pragma unroll
-                for (int x = 0; x < 4; ++x)
-                    if (gx + x < W) {
-                        o[x] = res[j][x];
-                        n_nan += (res[j][x] != res[j][x]);
-                    }
-            }
-        }
-    }
-    return n_nan;
-}
-
-// Replicate the grid border into the part of the tile's 1-cell halo that lies outside the grid
-// (cv2 BORDER_REPLICATE).  Only tiles touching the grid border have such cells.
-__device__ __forceinline__ void replicate_border(float* __restrict__ s_fill, int ty0, int tx0, int H, int W) {
-    if (ty0 > 0 && tx0 > 0 && ty0 + TH < H && tx0 + TW < W) return;  // interior tile (block-uniform)
-    for (int i = threadIdx.x; i < (TH + 2) * (TW + 2); i += kThreads) {
-        const int r = 1 + i / (TW + 2), c = 1 + i % (TW + 2);
-        const int gy = ty0 - 2 + r, gx = tx0 - 2 + c;
-        if (gy < 0 || gy >= H || gx < 0 || gx >= W) {
-            const int cy = min(max(gy, 0), H - 1), cx = min(max(gx, 0), W - 1);
-            const int rr = cy - (ty0 - 2), cc = cx - (tx0 - 2);
-            if (rr >= 1 && rr <= TH + 2 && cc >= 1 && cc <= TW + 2) s_fill[r * TS + OFF + c] = s_fill[rr * TS + OFF + cc];
-        }
-    }
-}
 
 template <typename Key>
 __global__ void __launch_bounds__(kThreads)
@@ -184,14 +28,11 @@ k_grid_finalize(const Key* __restrict__ keygrid, int W, int H, typename KeyTrait
     __shared__ __align__(16) float s_fill32[kSameTile ? 4 : TR * TS];  // float32 copy for the f64 path
     __shared__ unsigned short s_hole_pos[MAX_HOLES];
     __shared__ float s_hole_val[kSameTile ? MAX_HOLES : 1];
-    __shared__ int s_nholes, s_has_nan;
+    __shared__ int s_has_nan;
     float* s_fill = kSameTile ? reinterpret_cast<float*>(s_raw) : s_fill32;
     const int tid = threadIdx.x;
     const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH;
-    if (tid == 0) {
-        s_nholes = 0;
-        s_has_nan = 0;
-    }
+    if (tid == 0) s_has_nan = 0;
     __syncthreads();
 
     // 1. decode keys (+2 halo).  Key 0 (= empty, also used outside the grid) decodes to NaN, and the fill only
@@ -199,8 +40,9 @@ k_grid_finalize(const Key* __restrict__ keygrid, int W, int H, typename KeyTrait
     //    appended to a list with one shared atomic per warp-row (ballot-aggregated).
     //    Warp w loads tile rows w, w+8, ...; lane l takes columns l, l+32 and (l < 4) l+64: no div/mod, and the
     //    row address is computed once per row.
+    const int warp = tid >> 5, lane = tid & 31;
+    int wcnt = 0;   // holes listed by this warp (warp-uniform)
     {
-        const int warp = tid >> 5, lane = tid & 31;
         constexpr int NIT = (TR + 7) / 8;   // rows per warp
         // 1a. issue every global load of this thread before touching the results (memory-level parallelism: the
         //     phase is latency-bound otherwise)
@@ -220,7 +62,7 @@ k_grid_finalize(const Key* __restrict__ keygrid, int W, int H, typename KeyTrait
                 keys[it][part] = key;
             }
         }
-        // 1b. decode, store, list holes
+        // 1b. decode, store, list holes.  Every warp keeps its own hole list (count in a register, no atomics).
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
             const int r = warp + 8 * it;
@@ -242,10 +84,8 @@ k_grid_finalize(const Key* __restrict__ keygrid, int W, int H, typename KeyTrait
                     }
                     const unsigned m = __ballot_sync(0xffffffffu, hole);
                     if (m) {   // warp-uniform
-                        int base = 0;
-                        if (lane == 0) base = atomicAdd(&s_nholes, __popc(m));
-                        base = __shfl_sync(0xffffffffu, base, 0);
-                        if (hole) s_hole_pos[base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)pos;
+                        if (hole) s_hole_pos[warp * HSEG + wcnt + __popc(m & ((1u << lane) - 1u))] = (unsigned short)pos;
+                        wcnt += __popc(m);
                     }
                 }
             }
@@ -256,16 +96,16 @@ k_grid_finalize(const Key* __restrict__ keygrid, int W, int H, typename KeyTrait
     // 2. hole fill: NaN cell <- median of its non-NaN 3x3 neighbours in the PRE-fill grid, dense over the list.
     //    The fill must not cascade (lib/proj_to_grid.py:65 reads a copy): with one shared tile the results are
     //    staged and patched in after a barrier; the float64 path reads s_raw and writes the separate float32 tile.
-    const int nholes = s_nholes;
-    if (nholes > 0) {   // block-uniform
-        for (int h = tid; h < nholes; h += kThreads) {
-            const int pos = s_hole_pos[h];
+    {
+        bool nan_left = false;
+        for (int i = lane; i < wcnt; i += 32) {
+            const int pos = s_hole_pos[warp * HSEG + i];
             const T* c = s_raw + pos;
             T nb[8] = {c[-TS - 1], c[-TS], c[-TS + 1], c[-1], c[1], c[TS - 1], c[TS], c[TS + 1]};
             const T v = vs_median_of_valid8<T>(nb);
-            if (v != v) s_has_nan = 1;
+            nan_left |= (v != v);
             if (kSameTile) {
-                s_hole_val[h] = (float)v;
+                s_hole_val[warp * HSEG + i] = (float)v;
             } else {
                 s_fill[pos] = (float)v;
                 if (filled_out != nullptr) {
@@ -275,9 +115,10 @@ k_grid_finalize(const Key* __restrict__ keygrid, int W, int H, typename KeyTrait
                 }
             }
         }
+        if (nan_left) s_has_nan = 1;
         __syncthreads();
         if (kSameTile) {
-            for (int h = tid; h < nholes; h += kThreads) s_fill[s_hole_pos[h]] = s_hole_val[h];
+            for (int i = lane; i < wcnt; i += 32) s_fill[s_hole_pos[warp * HSEG + i]] = s_hole_val[warp * HSEG + i];
             __syncthreads();
         }
     }
@@ -357,9 +198,10 @@ k_median3x3(const float* __restrict__ in, int in_row0, int H, int W, int row_beg
     block_count_flush(n_nan, nan_count);
 }
 
-inline int simd_cols_for(int W, int simd_lanes) { return (simd_lanes > 0 && W >= simd_lanes + 2) ? 1 : 0; }
-
 }  // namespace
+
+int vs_finalize_tma_try(vs_ctx* ctx, bool keys, const void* in, int in_rows, int in_row0, int W, int H, int row_begin,
+                        int row_end, float* out, int simd_cols, unsigned long long* nan_count, cudaStream_t stream);
 
 extern "C" {
 
@@ -373,6 +215,13 @@ int vs_grid_finalize(vs_ctx* ctx, const uint32_t* keygrid, int32_t xsize, int32_
     if (!guard.ok) return vs_cuda_fail(cudaGetLastError(), "cudaSetDevice");
     cudaStream_t stream = (cudaStream_t)stream_;
     if (nan_count) VS_CUDA(cudaMemsetAsync(nan_count, 0, sizeof(uint64_t), stream));
+    if (!ctx->no_tma) {   // Blackwell path: persistent CTAs fed by TMA (finalize_tma.cu)
+        const int r = vs_finalize_tma_try(ctx, true, keygrid, ysize, 0, xsize, ysize, 0, ysize, dsm_out,
+                                          simd_cols_for(xsize, simd_lanes),
+                                          reinterpret_cast<unsigned long long*>(nan_count), stream);
+        if (r < 0) return VS_ERR_CUDA;
+        if (r > 0) return VS_OK;
+    }
     dim3 grid((xsize + TW - 1) / TW, (ysize + TH - 1) / TH);
     k_grid_finalize<uint32_t><<<grid, kThreads, 0, stream>>>(keygrid, xsize, ysize, nullptr, dsm_out,
                                                             simd_cols_for(xsize, simd_lanes),
@@ -411,6 +260,14 @@ int vs_median3x3(vs_ctx* ctx, const float* in, int32_t in_row0, int32_t H_total,
     if (nan_count) VS_CUDA(cudaMemsetAsync(nan_count, 0, sizeof(uint64_t), stream));
     if (row_begin == row_end) return VS_OK;
     VS_REQUIRE(in != nullptr && out != nullptr, "vs_median3x3: NULL array");
+    if (!ctx->no_tma) {
+        const int in_rows = (row_end + 1 < H_total ? row_end + 1 : H_total) - in_row0;
+        const int r = vs_finalize_tma_try(ctx, false, in, in_rows, in_row0, W, H_total, row_begin, row_end, out,
+                                          simd_cols_for(W, simd_lanes),
+                                          reinterpret_cast<unsigned long long*>(nan_count), stream);
+        if (r < 0) return VS_ERR_CUDA;
+        if (r > 0) return VS_OK;
+    }
     dim3 grid((W + TW - 1) / TW, (row_end - row_begin + TH - 1) / TH);
     k_median3x3<<<grid, kThreads, 0, stream>>>(in, in_row0, H_total, W, row_begin, row_end, out,
                                                simd_cols_for(W, simd_lanes),

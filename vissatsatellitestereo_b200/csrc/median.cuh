@@ -45,14 +45,15 @@ __device__ __forceinline__ double vs_max_t(double a, double b) { return fmax(a, 
 // odd k -> middle element, even k -> mean of the two middle elements (computed in double, as numpy does
 // for a float64 list), k == 0 -> NaN.  T is float (32-bit key path) or double (64-bit key path).
 template <typename T>
-__device__ __forceinline__ T vs_median_of_valid8(T v[8]) {
+__device__ __forceinline__ T vs_median_of_valid8(T (&v)[8]) {
     int k = 0;
     const T big = (T)CUDART_INF;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        if (v[i] == v[i]) ++k; else v[i] = big;   // NaN -> +inf sorts last
+    for (int i = 0; i < 8; ++i) {   // branch-free: NaN -> +inf sorts last
+        const bool ok = (v[i] == v[i]);
+        k += ok ? 1 : 0;
+        v[i] = ok ? v[i] : big;
     }
-    if (k == 0) return (T)CUDART_NAN;
     // Batcher odd-even merge sort for 8 inputs (19 exchanges); values are NaN-free here
 #define VS_CE(i, j) { const T lo = vs_min_t(v[i], v[j]); const T hi = vs_max_t(v[i], v[j]); v[i] = lo; v[j] = hi; }
     VS_CE(0, 1) VS_CE(2, 3) VS_CE(4, 5) VS_CE(6, 7)
@@ -62,13 +63,15 @@ __device__ __forceinline__ T vs_median_of_valid8(T v[8]) {
     VS_CE(2, 4) VS_CE(3, 5)
     VS_CE(1, 2) VS_CE(3, 4) VS_CE(5, 6)
 #undef VS_CE
+    // middle elements of the k valid ones: positions (k-1)/2 and k/2, i.e. <= 4, so v[5..7] are never read
     const int ilo = (k - 1) >> 1, ihi = k >> 1;
     T lo = v[0], hi = v[0];
 #pragma unroll
-    for (int i = 1; i < 8; ++i) {
+    for (int i = 1; i <= 4; ++i) {
         lo = (i == ilo) ? v[i] : lo;
         hi = (i == ihi) ? v[i] : hi;
     }
-    if (ilo == ihi) return hi;
-    return (T)(((double)lo + (double)hi) / 2.0);
+    const T avg = (T)(((double)lo + (double)hi) * 0.5);   // exact halving; == (lo + hi) / 2.0 in float64
+    const T med = (ilo == ihi) ? hi : avg;
+    return k == 0 ? (T)CUDART_NAN : med;
 }

@@ -54,6 +54,7 @@ struct vs_ctx {
     double* d_scratch;
     size_t scratch_doubles;
     void* d_exact;  // VsExactParams on the device (geo_chain.cuh)
+    bool no_tma;    // true unless VISSAT_TMA=1: stage B uses the plain-load kernels (see api.cu)
     // optional per-view kernel timing of vs_views_to_dsm
     bool timing;
     std::vector<cudaEvent_t> ev_pool;   // 3 events per logged view: before A, between A and B, after B
@@ -109,9 +110,10 @@ __host__ __device__ __forceinline__ uint32_t vs_key32(float f) {
     return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 __device__ __forceinline__ float vs_unkey32(uint32_t k) {
-    // k == 0 -> NaN (empty cell)
-    uint32_t b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
-    return __uint_as_float(b);  // k==0 -> 0xffffffff = NaN
+    // top bit set: clear it; top bit clear: invert everything.  Branch-free: k ^ (0x80000000 | ~sign_mask).
+    // k == 0 -> 0xffffffff = NaN (empty cell)
+    const uint32_t m = (uint32_t)((int32_t)k >> 31);          // 0xffffffff if the top bit is set
+    return __uint_as_float(k ^ (0x80000000u | ~m));
 }
 __device__ __forceinline__ unsigned long long vs_key64(double d) {
     unsigned long long b = (unsigned long long)__double_as_longlong(d);
