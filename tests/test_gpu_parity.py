@@ -301,3 +301,40 @@ def test_errors_are_loud(eng_mod):
         ctx.set_aoi(bad)
     with pytest.raises(_native.VisSatError):
         _native.Context(9999)
+
+
+def test_tma_pipeline_variant_is_bit_identical(golden, eng_mod, lanes, monkeypatch):
+    """VISSAT_TMA=1 routes stage B (and the final blur) through the TMA-fed persistent kernels; results must be
+    bit-identical to the plain-load kernels (and therefore to the reference-pinned expectations above)."""
+    case = 'c3'
+    aoi = json.loads(str(golden[case + '_aoi']))
+    res = float(golden[case + '_res'])
+    depths, mats = golden[case + '_depths'], golden[case + '_mats']
+    plain = eng_mod.DsmEngine(aoi, res, res, simd_lanes=lanes)
+    monkeypatch.setenv('VISSAT_TMA', '1')
+    tma = eng_mod.DsmEngine(aoi, res, res, simd_lanes=lanes)          # the flag is read when the context is created
+    monkeypatch.delenv('VISSAT_TMA')
+    assert plain.e_size % 4 == 0                                      # TMA path applicable (row pitch multiple of 16 B)
+    views_a, views_b = [], []
+    for v in range(depths.shape[0]):
+        d = torch.from_numpy(depths[v]).cuda()
+        views_a.append(plain.view_dsm(d, mats[v]).clone())
+        views_b.append(tma.view_dsm(d, mats[v]).clone())
+        assert torch.equal(torch.nan_to_num(views_a[-1], nan=-1e9), torch.nan_to_num(views_b[-1], nan=-1e9)), v
+    fa = plain.fuse_and_blur(torch.stack(views_a))
+    fb = tma.fuse_and_blur(torch.stack(views_b))
+    assert torch.equal(torch.nan_to_num(fa, nan=-1e9), torch.nan_to_num(fb, nan=-1e9))
+    assert _eq(fb.cpu().numpy(), op.fuse_dsms([v.cpu().numpy() for v in views_a]))
+    assert plain.last_nan_count() == tma.last_nan_count()
+    # random NaN-heavy images through both blur kernels, incl. row bands
+    rng = np.random.default_rng(11)
+    for shape in [(64, 64), (100, 132), (257, 260)]:
+        img = rng.normal(size=shape).astype(np.float32)
+        img[rng.random(shape) < 0.3] = np.nan
+        t = torch.from_numpy(img).cuda()
+        want = cv2.medianBlur(img, 3)
+        assert _eq(tma.median3x3(t).cpu().numpy(), want)
+        r0, r1 = 5, shape[0] - 7
+        band = t[r0 - 1:r1 + 1].contiguous()
+        got = tma.median3x3(band, row_begin=r0, row_end=r1, in_row0=r0 - 1, h_total=shape[0]).cpu().numpy()
+        assert _eq(got, want[r0:r1])
