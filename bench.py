@@ -113,7 +113,7 @@ def _cpu_view_worker(args):
     return dsm
 
 
-def cpu_sample(cfg, n_views, band_rows, cores, geo=None):
+def cpu_sample(cfg, n_views, band_rows, cores, geo=None, shrink=1):
     """Time the oracle (CPU restatement of the reference) on a bounded sample of the workload and extrapolate
     linearly to the whole config: n_views views through the per-view stage with a
     multiprocessing.Pool(cores) exactly like aggregate_2p5d_util.py:138-146, then the single-process fusion
@@ -121,6 +121,11 @@ def cpu_sample(cfg, n_views, band_rows, cores, geo=None):
     import multiprocessing as mp
     from oracle import geodesy, pipeline as op
     from vissatsatellitestereo_b200 import synthetic as S
+    full = cfg
+    if shrink > 1:
+        # same recipe on a sub-AOI: depth maps and grid both 1/shrink in each dimension (same GSD, same density);
+        # every stage is linear in pixels / cells, so the throughput is extrapolated by area
+        cfg = S.scaled(cfg, depth=cfg.height // shrink, grid=cfg.e_size // shrink, name=cfg.name)
     scene = S.make_scene(cfg, geodesy, device='cpu', views=range(n_views))
     jobs = [(d.numpy(), M, scene.aoi, cfg.res) for d, M in zip(scene.depths, scene.mats)]
     t0 = time.perf_counter()
@@ -135,12 +140,16 @@ def cpu_sample(cfg, n_views, band_rows, cores, geo=None):
         op.fuse_dsms(cube)
         t_fuse = time.perf_counter() - t0
     n_rows = dsms[0].shape[0]
-    total = t_views * (cfg.n_views / n_views) + t_fuse * (n_rows / max(band_rows, 1))
-    mpix = cfg.n_views * cfg.height * cfg.width / 1e6
+    area = float(shrink * shrink)
+    total = (t_views * (cfg.n_views / n_views) + t_fuse * (n_rows / max(band_rows, 1))) * area
+    mpix = full.n_views * full.height * full.width / 1e6
     return {'value': mpix / total, 't_views_s': t_views, 't_fuse_s': t_fuse, 'extrapolated_total_s': total,
-            'sample': '{} of {} views through the per-view stage (Pool({})), fusion on {} of {} grid rows x {} views; '
-                      'extrapolated linearly'.format(n_views, cfg.n_views, min(cores, n_views), band_rows, n_rows,
-                                                     cfg.n_views)}
+            'sample': '{} of {} views{} through the per-view stage (Pool({})), fusion on {} of {} grid rows x {} views; '
+                      'extrapolated linearly'.format(
+                          n_views, cfg.n_views,
+                          '' if shrink == 1 else ' on a 1/{0} x 1/{0} sub-AOI ({1}x{2} depth -> {3}x{4} grid)'.format(
+                              shrink, cfg.height, cfg.width, cfg.n_size, cfg.e_size),
+                          min(cores, n_views), band_rows, n_rows, cfg.n_views)}
 
 
 def run_reference_arm(args, cfg):
@@ -149,9 +158,11 @@ def run_reference_arm(args, cfg):
         return
     cores = os.cpu_count() or 1
     n_views = max(1, min(cores, cfg.n_views, 16))
+    # keep the whole run within a few minutes: ~25 s per full-size sample, ~6 s on a half-size sub-AOI
+    shrink = 1 if (args.warmup + args.steps) <= 4 or cfg.height <= 1024 else 2
     vals, last = [], None
     for i in range(args.warmup + args.steps):
-        last = cpu_sample(cfg, n_views, 32, cores)
+        last = cpu_sample(cfg, n_views, 32, cores, shrink=shrink)
         if i >= args.warmup:
             vals.append(last['value'])
     value = float(np.mean(vals))
