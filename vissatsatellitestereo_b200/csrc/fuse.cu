@@ -38,13 +38,17 @@ VS_DEF_SORTNET(40)
 VS_DEF_SORTNET(48)
 VS_DEF_SORTNET(56)
 VS_DEF_SORTNET(64)
+VS_DEF_SORTNET(80)
+VS_DEF_SORTNET(96)
+VS_DEF_SORTNET(112)
+VS_DEF_SORTNET(128)
 #undef VS_DEF_SORTNET
 
 // Bitonic merge (ascending) of a bitonic sequence held in N registers; N is padded to a power of two with
 // virtual +inf wires, whose compare-exchanges are no-ops and are skipped at compile time.
 template <int N>
 __device__ __forceinline__ void bitonic_merge_regs(float (&a)[N]) {
-    constexpr int N2 = N <= 8 ? 8 : N <= 16 ? 16 : N <= 32 ? 32 : 64;
+    constexpr int N2 = N <= 8 ? 8 : N <= 16 ? 16 : N <= 32 ? 32 : N <= 64 ? 64 : 128;
 #pragma unroll
     for (int j = N2 / 2; j > 0; j >>= 1) {
 #pragma unroll
@@ -147,17 +151,8 @@ k_fuse_small(const float* __restrict__ views, int64_t plane_stride, int V, int64
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// large V (65..2048): LANES threads per cell.
-//
-// 1. The CTA loads its cells x V tile with coalesced 128-byte rows into shared memory.
-// 2. Lane l of a cell takes values v = l, l+LANES, ... (<= NVL of them), sorts them in registers with the same
-//    merge-exchange network as the small path and writes them back as a sorted run of order-preserving keys.
-// 3. Order statistics of the union of the LANES runs come from a 32-step bitwise bisection on the key; each
-//    step is one branch-free lower_bound per lane (<= 7 shared-memory probes) and a shuffle reduction.
-// 4. For the MAD each lane turns its sorted run into |x - med| (bitonic), merges it in registers, and the same
-//    bisection runs on those runs.
-// 5. The float32 sum in numpy's pairwise order is accumulated by lanes 0..7 of the cell (numpy's 8 strided
-//    accumulators), re-reading the views from L2.
+// medium V (65..128): still one thread per cell and a register sorting network, but only the SORTED copy lives
+// in registers; the original-order values needed by the pairwise sum are re-read from L2 (KeepFn).
 // ---------------------------------------------------------------------------------------------------------
 struct KeepFn {
     const float* p;
@@ -175,6 +170,70 @@ struct KeepFn {
     }
 };
 
+template <int NV>
+__global__ void __launch_bounds__(kBlockSmall)
+k_fuse_medium(const float* __restrict__ views, int64_t plane_stride, int V, int64_t n_cells, float* __restrict__ out) {
+    const int64_t cell = blockIdx.x * (int64_t)kBlockSmall + threadIdx.x;
+    if (cell >= n_cells) return;
+    float s[NV];
+    int k = 0;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        float t = CUDART_NAN_F;
+        if (v < V) t = __ldg(views + (int64_t)v * plane_stride + cell);
+        const bool ok = (t == t);
+        k += ok;
+        s[v] = ok ? t : CUDART_INF_F;
+    }
+    if (k <= 2) {  // :69-71
+        out[cell] = CUDART_NAN_F;
+        return;
+    }
+    SortNet<NV>::sort(s);
+    const float med = middle_of_sorted<NV>(s, k);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) s[v] = fabsf(__fsub_rn(s[v], med));
+    bitonic_merge_regs<NV>(s);
+    const float mad = middle_of_sorted<NV>(s, k);
+    // numpy pairwise sum for 8 <= V <= 128: one leaf, 8 strided accumulators, then the tail
+    const KeepFn y{views + cell, plane_stride, med, mad};
+    int cnt = 0;
+    float r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        r[j] = y(j);
+        cnt += y.kept(j);
+    }
+    const int nfull = V - (V & 7);
+    for (int i = 8; i < nfull; i += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            r[j] = __fadd_rn(r[j], y(i + j));
+            cnt += y.kept(i + j);
+        }
+    }
+    float tot = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                          __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+    for (int i = nfull; i < V; ++i) {
+        tot = __fadd_rn(tot, y(i));
+        cnt += y.kept(i);
+    }
+    out[cell] = __fdiv_rn(tot, (float)cnt);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// large V (129..2048): LANES threads per cell.
+//
+// 1. The CTA loads its cells x V tile with coalesced 128-byte rows into shared memory.
+// 2. Lane l of a cell takes values v = l, l+LANES, ... (<= NVL of them), sorts them in registers with the same
+//    merge-exchange network as the small path and writes them back as a sorted run of order-preserving keys.
+// 3. Order statistics of the union of the LANES runs come from a 32-step bitwise bisection on the key; each
+//    step is one branch-free lower_bound per lane (<= 7 shared-memory probes) and a shuffle reduction.
+// 4. For the MAD each lane turns its sorted run into |x - med| (bitonic), merges it in registers, and the same
+//    bisection runs on those runs.
+// 5. The float32 sum in numpy's pairwise order is accumulated by lanes 0..7 of the cell (numpy's 8 strided
+//    accumulators), re-reading the views from L2.
+// ---------------------------------------------------------------------------------------------------------
 constexpr int kLargeThreads = 256;
 
 template <int LANES>
@@ -193,7 +252,7 @@ __device__ __forceinline__ uint32_t group_max(uint32_t v, unsigned mask) {
 // number of keys < T in this lane's sorted run (NVL keys, stride LANES)
 template <int LANES, int NVL>
 __device__ __forceinline__ int run_lower_bound(const uint32_t* __restrict__ run, uint32_t T) {
-    constexpr int P = NVL >= 64 ? 64 : NVL >= 32 ? 32 : NVL >= 16 ? 16 : 8;
+    constexpr int P = NVL >= 128 ? 128 : NVL >= 64 ? 64 : NVL >= 32 ? 32 : NVL >= 16 ? 16 : 8;
     int lb = 0;
 #pragma unroll
     for (int step = P; step >= 1; step >>= 1) {
@@ -377,6 +436,15 @@ int launch_small(vs_ctx* ctx, const float* views, int64_t plane_stride, int V, i
     return VS_OK;
 }
 
+template <int NV>
+int launch_medium(vs_ctx* ctx, const float* views, int64_t plane_stride, int V, int64_t n_cells, float* out,
+                  cudaStream_t stream) {
+    const int64_t blocks = (n_cells + kBlockSmall - 1) / kBlockSmall;
+    k_fuse_medium<NV><<<(unsigned)blocks, kBlockSmall, 0, stream>>>(views, plane_stride, V, n_cells, out);
+    VS_CHECK_LAUNCH(ctx, "k_fuse_medium");
+    return VS_OK;
+}
+
 template <int LANES, int NVL>
 int launch_large_t(vs_ctx* ctx, const float* views, int64_t plane_stride, int V, int64_t n_cells, float* out,
                    cudaStream_t stream) {
@@ -395,7 +463,8 @@ int launch_large(vs_ctx* ctx, const float* views, int64_t plane_stride, int V, i
                  cudaStream_t stream) {
 #define VS_TRY(LANES, NVL) \
     if (V <= LANES * NVL) return launch_large_t<LANES, NVL>(ctx, views, plane_stride, V, n_cells, out, stream);
-    VS_TRY(2, 40) VS_TRY(2, 48) VS_TRY(2, 56) VS_TRY(2, 64)
+    // runs of 40..64 values per lane: longer register-sorted runs (80..128) were measured 2x slower (255 registers
+    // and > 100 KB of shared memory per CTA leave one CTA per SM)
     VS_TRY(4, 40) VS_TRY(4, 48) VS_TRY(4, 56) VS_TRY(4, 64)
     VS_TRY(8, 40) VS_TRY(8, 48) VS_TRY(8, 56) VS_TRY(8, 64)
     VS_TRY(32, 24) VS_TRY(32, 32) VS_TRY(32, 48) VS_TRY(32, 64)
@@ -428,6 +497,10 @@ extern "C" int vs_fuse_views(vs_ctx* ctx, const float* views, int64_t plane_stri
     if (V <= 48) return launch_small<48>(ctx, views, plane_stride, V, n_cells, out_mean, stream);
     if (V <= 56) return launch_small<56>(ctx, views, plane_stride, V, n_cells, out_mean, stream);
     if (V <= 64) return launch_small<64>(ctx, views, plane_stride, V, n_cells, out_mean, stream);
+    if (V <= 80) return launch_medium<80>(ctx, views, plane_stride, V, n_cells, out_mean, stream);
+    if (V <= 96) return launch_medium<96>(ctx, views, plane_stride, V, n_cells, out_mean, stream);
+    if (V <= 112) return launch_medium<112>(ctx, views, plane_stride, V, n_cells, out_mean, stream);
+    if (V <= 128) return launch_medium<128>(ctx, views, plane_stride, V, n_cells, out_mean, stream);
     return launch_large(ctx, views, plane_stride, V, n_cells, out_mean, stream);
 }
 
