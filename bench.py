@@ -319,28 +319,46 @@ def run_b200_arm(args, cfg):
     # ---- e2e: pinned host depth maps -> H2D -> kernels -> D2H of per-view DSMs + fused DSM, every step
     e2e = None
     clocks = sampler.stop() if rank == 0 else None
-    if world == 1:
+    if True:
         host_depths = [d.cpu().pin_memory() for d in depths]
         host_views = torch.empty((V, eng.n_size, eng.e_size), dtype=torch.float32).pin_memory()
-        host_fused = torch.empty((eng.n_size, eng.e_size), dtype=torch.float32).pin_memory()
+        rows_mine = eng.n_size if world == 1 else (lambda b: b[1] - b[0])(D.row_bands(eng.n_size, world)[rank])
+        host_fused = torch.empty((rows_mine, eng.e_size), dtype=torch.float32).pin_memory()
+
+        def e2e_step():
+            if world == 1:
+                eng.process_host(host_depths, mats, host_views, host_fused, stack=stack, fuse=cfg.fuse)
+                return
+            # every rank: its views host -> device -> per-view DSMs -> host; then exchange, fuse own band, band -> host
+            eng.process_host(host_depths, mats, host_views, None, stack=stack, fuse=False)
+            if cfg.fuse:
+                band, _ = D.fuse_distributed(eng, stack, view_counts)
+                host_fused.copy_(band, non_blocking=True)
+                torch.cuda.synchronize()
+
         for _ in range(max(1, min(args.warmup, 2))):
-            eng.process_host(host_depths, mats, host_views, host_fused, stack=stack, fuse=cfg.fuse)
+            e2e_step()
         n_e2e = max(1, min(args.steps, 5))
-        torch.cuda.synchronize()
+        barrier()
         w0 = time.perf_counter()
         e0, e1 = ev(), ev()
         e0.record()
         for _ in range(n_e2e):
-            eng.process_host(host_depths, mats, host_views, host_fused, stack=stack, fuse=cfg.fuse)
+            e2e_step()
         e1.record()
-        torch.cuda.synchronize()
+        barrier()
         wall = (time.perf_counter() - w0) / n_e2e
         dev_ms = e0.elapsed_time(e1) / n_e2e
         t_e2e = max(wall, dev_ms * 1e-3)
-        e2e = {'value': mpix_step / t_e2e, 'unit': UNIT, 'h2d_bytes_per_step': int(V * P * 4),
-               'd2h_bytes_per_step': int(V * G * 4 + (G * 4 if cfg.fuse else 0)), 'ms_per_step': 1e3 * t_e2e,
-               'steps': n_e2e, 'api': 'DsmEngine.process_host (pinned host buffers in/out, 3 streams)'}
-        if cfg.fuse:
+        if world > 1:
+            t = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_e2e = float(t.item())
+        e2e = {'value': mpix_step / t_e2e, 'unit': UNIT, 'h2d_bytes_per_step': int(V * P * 4) * world,
+               'd2h_bytes_per_step': int(V * G * 4) * world + (G * 4 if cfg.fuse else 0), 'ms_per_step': 1e3 * t_e2e,
+               'steps': n_e2e, 'api': 'DsmEngine.process_host (pinned host buffers in/out, 3 streams)' +
+               ('' if world == 1 else ' per rank + NCCL row-band exchange + per-rank fused band to host')}
+        if cfg.fuse and world == 1:
             assert np.array_equal(host_fused.numpy(), fused.cpu().numpy(), equal_nan=True), 'e2e result differs'
 
     if rank != 0:
