@@ -42,7 +42,53 @@ k_grid_finalize(const Key* __restrict__ keygrid, int W, int H, typename KeyTrait
     //    row address is computed once per row.
     const int warp = tid >> 5, lane = tid & 31;
     int wcnt = 0;   // holes listed by this warp (warp-uniform)
-    {
+    // Interior tiles of a grid whose rows are 16-byte multiples: the 36 x 72 box (grid columns tx0-4 .. tx0+67) is
+    // fetched with 16-byte loads, 18 per row.  Edge tiles (and odd pitches) take the scalar, bounds-checked loader.
+    const bool vec_ok = sizeof(Key) == 4 && (W & 3) == 0 && ((reinterpret_cast<uintptr_t>(keygrid) & 15) == 0) &&
+                        tx0 >= 4 && tx0 + TW + 4 <= W && ty0 >= 2 && ty0 + TH + 2 <= H;
+    if (vec_ok) {
+        constexpr int VPR = TS / 4;                 // 18 vectors per row
+        constexpr int NV4 = (TR * VPR + kThreads - 1) / kThreads;   // 3 per thread
+        uint4 kv[NV4];
+#pragma unroll
+        for (int q = 0; q < NV4; ++q) {             // all loads first
+            const int i = tid + q * kThreads;
+            const int r = i / VPR, v4 = i - r * VPR;
+            kv[q] = make_uint4(0u, 0u, 0u, 0u);
+            if (i < TR * VPR)
+                kv[q] = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint32_t*>(keygrid) +
+                                                       (size_t)(ty0 - 2 + r) * W + (tx0 - 4) + 4 * v4);
+        }
+#pragma unroll
+        for (int q = 0; q < NV4; ++q) {
+            const int i = tid + q * kThreads;
+            const int r = i / VPR, v4 = i - r * VPR;
+            const bool act = i < TR * VPR;
+            const uint32_t kk[4] = {kv[q].x, kv[q].y, kv[q].z, kv[q].w};
+            const int pos0 = r * TS + 4 * v4;       // box column 4*v4 <-> tile column 4*v4 - OFF
+            if (act) {
+                float4 f = make_float4(vs_unkey32(kk[0]), vs_unkey32(kk[1]), vs_unkey32(kk[2]), vs_unkey32(kk[3]));
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(s_raw) + pos0) = f;
+            }
+            const bool row_in = act && (unsigned)(r - 1) < (unsigned)(TH + 2);
+            bool h4[4];
+            bool any_h = false;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int c = 4 * v4 + e - OFF;     // tile column
+                h4[e] = row_in && kk[e] == 0 && (unsigned)(c - 1) < (unsigned)(TW + 2);
+                any_h |= h4[e];
+            }
+            if (__any_sync(0xffffffffu, any_h)) {   // warp-uniform
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const unsigned m = __ballot_sync(0xffffffffu, h4[e]);
+                    if (h4[e]) s_hole_pos[warp * HSEG2 + wcnt + __popc(m & ((1u << lane) - 1u))] = (unsigned short)(pos0 + e);
+                    wcnt += __popc(m);
+                }
+            }
+        }
+    } else {
         constexpr int NIT = (TR + 7) / 8;   // rows per warp
         // 1a. issue every global load of this thread before touching the results (memory-level parallelism: the
         //     phase is latency-bound otherwise)
@@ -84,7 +130,7 @@ k_grid_finalize(const Key* __restrict__ keygrid, int W, int H, typename KeyTrait
                     }
                     const unsigned m = __ballot_sync(0xffffffffu, hole);
                     if (m) {   // warp-uniform
-                        if (hole) s_hole_pos[warp * HSEG + wcnt + __popc(m & ((1u << lane) - 1u))] = (unsigned short)pos;
+                        if (hole) s_hole_pos[warp * HSEG2 + wcnt + __popc(m & ((1u << lane) - 1u))] = (unsigned short)pos;
                         wcnt += __popc(m);
                     }
                 }
@@ -99,13 +145,13 @@ k_grid_finalize(const Key* __restrict__ keygrid, int W, int H, typename KeyTrait
     {
         bool nan_left = false;
         for (int i = lane; i < wcnt; i += 32) {
-            const int pos = s_hole_pos[warp * HSEG + i];
+            const int pos = s_hole_pos[warp * HSEG2 + i];
             const T* c = s_raw + pos;
             T nb[8] = {c[-TS - 1], c[-TS], c[-TS + 1], c[-1], c[1], c[TS - 1], c[TS], c[TS + 1]};
             const T v = vs_median_of_valid8<T>(nb);
             nan_left |= (v != v);
             if (kSameTile) {
-                s_hole_val[warp * HSEG + i] = (float)v;
+                s_hole_val[warp * HSEG2 + i] = (float)v;
             } else {
                 s_fill[pos] = (float)v;
                 if (filled_out != nullptr) {
@@ -118,7 +164,7 @@ k_grid_finalize(const Key* __restrict__ keygrid, int W, int H, typename KeyTrait
         if (nan_left) s_has_nan = 1;
         __syncthreads();
         if (kSameTile) {
-            for (int i = lane; i < wcnt; i += 32) s_fill[s_hole_pos[warp * HSEG + i]] = s_hole_val[warp * HSEG + i];
+            for (int i = lane; i < wcnt; i += 32) s_fill[s_hole_pos[warp * HSEG2 + i]] = s_hole_val[warp * HSEG2 + i];
             __syncthreads();
         }
     }
@@ -150,7 +196,32 @@ k_median3x3(const float* __restrict__ in, int in_row0, int H, int W, int row_beg
     if (tid == 0) s_has_nan = 0;
     __syncthreads();
     bool saw_nan = false;
-    {
+    const bool vec_ok = (W & 3) == 0 && ((reinterpret_cast<uintptr_t>(in) & 15) == 0) && tx0 >= 4 && tx0 + TW + 4 <= W &&
+                        ty0 >= 1 && ty0 + TH <= row_end && ty0 + TH <= H - 1;
+    if (vec_ok) {   // interior tile: rows ty0-1 .. ty0+TH, grid columns tx0-4 .. tx0+67, 16-byte loads
+        constexpr int VPR = TS / 4;
+        constexpr int NROW = TH + 2;
+        constexpr int NV4 = (NROW * VPR + kThreads - 1) / kThreads;
+        float4 fv[NV4];
+#pragma unroll
+        for (int q = 0; q < NV4; ++q) {
+            const int i = tid + q * kThreads;
+            const int r = 1 + i / VPR, v4 = i - (r - 1) * VPR;
+            fv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < NROW * VPR)
+                fv[q] = *reinterpret_cast<const float4*>(in + (size_t)(ty0 - 2 + r - in_row0) * W + (tx0 - 4) + 4 * v4);
+        }
+#pragma unroll
+        for (int q = 0; q < NV4; ++q) {
+            const int i = tid + q * kThreads;
+            const int r = 1 + i / VPR, v4 = i - (r - 1) * VPR;
+            if (i < NROW * VPR) {
+                *reinterpret_cast<float4*>(s_fill + r * TS + 4 * v4) = fv[q];
+                const float sum = (fv[q].x + fv[q].y) + (fv[q].z + fv[q].w);
+                saw_nan |= !(sum == sum);       // conservative (also the 2 unused columns on each side)
+            }
+        }
+    } else {
         const int warp = tid >> 5, lane = tid & 31;
         constexpr int NIT = (TH + 2 + 7) / 8;
         float vals[NIT][3];

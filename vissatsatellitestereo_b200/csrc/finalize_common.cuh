@@ -20,7 +20,8 @@ constexpr int TS = 72;            // shared row stride in elements (>= OFF + TW 
 constexpr int TR = TH + 4;        // shared rows (halo 2)
 constexpr int TC = TW + 4;        // shared columns in use (halo 2)
 constexpr int HSEG = ((TR + 7) / 8) * (TW + 2) + 6;   // hole-list capacity per warp (its rows x inner columns), 336
-constexpr int MAX_HOLES = 8 * HSEG;
+constexpr int HSEG2 = 392;                             // capacity per warp in finalize.cu (its vector path lists up to 3*32*4 cells per warp)
+constexpr int MAX_HOLES = 8 * HSEG2;
 
 template <typename Key> struct KeyTraits;
 template <> struct KeyTraits<uint32_t> {
