@@ -18,6 +18,23 @@ using namespace vsfin;
 
 namespace {
 
+// all-empty tile: every output is NaN (hole fill and blur of nothing)
+template <typename T>
+__device__ __forceinline__ void write_nan_tile(float* __restrict__ blur_out, T* __restrict__ filled_out, int ty0, int tx0,
+                                               int H, int W, unsigned long long* __restrict__ nan_count) {
+    unsigned n = 0;
+    for (int i = threadIdx.x; i < TW * TH; i += kThreads) {
+        const int r = i / TW, c = i - r * TW;
+        const int gy = ty0 + r, gx = tx0 + c;
+        if (gy < H && gx < W) {
+            if (blur_out != nullptr) blur_out[(size_t)gy * W + gx] = CUDART_NAN_F;
+            if (filled_out != nullptr) filled_out[(size_t)gy * W + gx] = (T)CUDART_NAN;
+            ++n;
+        }
+    }
+    if (blur_out != nullptr) block_count_flush(n, nan_count);
+}
+
 template <typename Key>
 __global__ void __launch_bounds__(kThreads)
 k_grid_finalize(const Key* __restrict__ keygrid, int W, int H, typename KeyTraits<Key>::value_t* __restrict__ filled_out,
@@ -58,6 +75,15 @@ k_grid_finalize(const Key* __restrict__ keygrid, int W, int H, typename KeyTrait
             if (i < TR * VPR)
                 kv[q] = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint32_t*>(keygrid) +
                                                        (size_t)(ty0 - 2 + r) * W + (tx0 - 4) + 4 * v4);
+        }
+        {   // a tile whose whole box is empty (large AOIs: most tiles of most views) is all-NaN: skip the work
+            unsigned nz = 0;
+#pragma unroll
+            for (int q = 0; q < NV4; ++q) nz |= kv[q].x | kv[q].y | kv[q].z | kv[q].w;
+            if (!__syncthreads_or(nz != 0)) {
+                write_nan_tile(blur_out, filled_out, ty0, tx0, H, W, nan_count);
+                return;
+            }
         }
 #pragma unroll
         for (int q = 0; q < NV4; ++q) {
@@ -106,6 +132,17 @@ k_grid_finalize(const Key* __restrict__ keygrid, int W, int H, typename KeyTrait
                 Key key = 0;
                 if (row_ok && (part < 2 || lane < TC - 64) && (unsigned)gx < (unsigned)W) key = row[c];
                 keys[it][part] = key;
+            }
+        }
+        {
+            bool nz = false;
+#pragma unroll
+            for (int it = 0; it < NIT; ++it)
+#pragma unroll
+                for (int part = 0; part < 3; ++part) nz |= (keys[it][part] != 0);
+            if (!__syncthreads_or(nz)) {
+                write_nan_tile(blur_out, filled_out, ty0, tx0, H, W, nan_count);
+                return;
             }
         }
         // 1b. decode, store, list holes.  Every warp keeps its own hole list (count in a register, no atomics).
