@@ -136,6 +136,15 @@ int vs_ctx_create(int device, vs_ctx** out) {
     ctx->scratch_doubles = 0;
     ctx->d_exact = nullptr;
     ctx->timing = false;
+    ctx->side_stream[0] = ctx->side_stream[1] = nullptr;
+    ctx->fork_event = nullptr;
+    ctx->join_event[0] = ctx->join_event[1] = nullptr;
+    ctx->d_keygrid2 = nullptr;
+    ctx->keygrid2_cells = 0;
+    {
+        const char* e1 = getenv("VISSAT_ONE_STREAM");
+        ctx->two_streams = !(e1 != nullptr && e1[0] == '1');
+    }
     {
         // The TMA-fed persistent variant of stage B (finalize_tma.cu) is bit-identical but measured slower than
         // the plain-load kernels on B200 (41.7 vs 34.3 us per 2048^2 view: its in-place decode is an extra
@@ -154,6 +163,12 @@ int vs_ctx_destroy(vs_ctx* ctx) {
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     if (ctx->d_exact) cudaFree(ctx->d_exact);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->side_stream[i]) cudaStreamDestroy(ctx->side_stream[i]);
+        if (ctx->join_event[i]) cudaEventDestroy(ctx->join_event[i]);
+    }
+    if (ctx->fork_event) cudaEventDestroy(ctx->fork_event);
+    if (ctx->d_keygrid2) cudaFree(ctx->d_keygrid2);
     delete ctx;
     return VS_OK;
 }

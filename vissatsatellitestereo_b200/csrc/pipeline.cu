@@ -27,20 +27,49 @@ int vs_views_to_dsm(vs_ctx* ctx, int32_t n_views, const float* const* depth, con
             ctx->ev_pool.push_back(e);
         }
     }
+    // Two internal streams: view v runs on stream v & 1 with its own key grid, so stage A (FP64/XU/issue-bound) of one
+    // view overlaps stage B (ALU-bound) of the previous one.  Fork from / join into the caller's stream with events.
+    const bool dual = ctx->two_streams && n_views >= 2;
+    if (dual) {
+        if (!ctx->side_stream[0]) {
+            for (int i = 0; i < 2; ++i) {
+                VS_CUDA(cudaStreamCreateWithFlags(&ctx->side_stream[i], cudaStreamNonBlocking));
+                VS_CUDA(cudaEventCreateWithFlags(&ctx->join_event[i], cudaEventDisableTiming));
+            }
+            VS_CUDA(cudaEventCreateWithFlags(&ctx->fork_event, cudaEventDisableTiming));
+        }
+        if (ctx->keygrid2_cells < (size_t)xs * ys) {
+            if (ctx->d_keygrid2) cudaFree(ctx->d_keygrid2);
+            ctx->d_keygrid2 = nullptr;
+            ctx->keygrid2_cells = 0;
+            VS_CUDA(cudaMalloc(&ctx->d_keygrid2, (size_t)xs * ys * sizeof(uint32_t)));
+            ctx->keygrid2_cells = (size_t)xs * ys;
+        }
+        VS_CUDA(cudaEventRecord(ctx->fork_event, stream));
+        for (int i = 0; i < 2; ++i) VS_CUDA(cudaStreamWaitEvent(ctx->side_stream[i], ctx->fork_event, 0));
+    }
     for (int v = 0; v < n_views; ++v) {
-        int rc = vs_keygrid_clear(ctx, keygrid, (int64_t)xs * ys, 4, stream_);
+        cudaStream_t st = dual ? ctx->side_stream[v & 1] : stream;
+        uint32_t* kg = (dual && (v & 1)) ? ctx->d_keygrid2 : keygrid;
+        int rc = vs_keygrid_clear(ctx, kg, (int64_t)xs * ys, 4, st);
         if (rc) return rc;
-        if (ctx->timing) VS_CUDA(cudaEventRecord(ctx->ev_pool[ctx->ev_used + 0], stream));
-        rc = vs_unproject_rasterize(ctx, depth[v], H[v], W[v], inv_proj_mats + 16 * (size_t)v, keygrid, 0, nullptr,
-                                    stats ? stats + (size_t)v * VS_NUM_STATS : nullptr, stream_);
+        if (ctx->timing) VS_CUDA(cudaEventRecord(ctx->ev_pool[ctx->ev_used + 0], st));
+        rc = vs_unproject_rasterize(ctx, depth[v], H[v], W[v], inv_proj_mats + 16 * (size_t)v, kg, 0, nullptr,
+                                    stats ? stats + (size_t)v * VS_NUM_STATS : nullptr, st);
         if (rc) return rc;
-        if (ctx->timing) VS_CUDA(cudaEventRecord(ctx->ev_pool[ctx->ev_used + 1], stream));
-        rc = vs_grid_finalize(ctx, keygrid, xs, ys, dsm_stack + (size_t)v * plane_stride, simd_lanes,
-                              nan_counts ? nan_counts + v : nullptr, stream_);
+        if (ctx->timing) VS_CUDA(cudaEventRecord(ctx->ev_pool[ctx->ev_used + 1], st));
+        rc = vs_grid_finalize(ctx, kg, xs, ys, dsm_stack + (size_t)v * plane_stride, simd_lanes,
+                              nan_counts ? nan_counts + v : nullptr, st);
         if (rc) return rc;
         if (ctx->timing) {
-            VS_CUDA(cudaEventRecord(ctx->ev_pool[ctx->ev_used + 2], stream));
+            VS_CUDA(cudaEventRecord(ctx->ev_pool[ctx->ev_used + 2], st));
             ctx->ev_used += 3;
+        }
+    }
+    if (dual) {
+        for (int i = 0; i < 2; ++i) {
+            VS_CUDA(cudaEventRecord(ctx->join_event[i], ctx->side_stream[i]));
+            VS_CUDA(cudaStreamWaitEvent(stream, ctx->join_event[i], 0));
         }
     }
     return VS_OK;

@@ -55,6 +55,13 @@ struct vs_ctx {
     size_t scratch_doubles;
     void* d_exact;  // VsExactParams on the device (geo_chain.cuh)
     bool no_tma;    // true unless VISSAT_TMA=1: stage B uses the plain-load kernels (see api.cu)
+    // vs_views_to_dsm runs odd and even views on two internal streams (stage A of one view overlaps stage B of the
+    // previous one: they are bound by different pipes); the odd views scatter into a second, library-owned key grid
+    cudaStream_t side_stream[2];
+    cudaEvent_t fork_event, join_event[2];
+    uint32_t* d_keygrid2;
+    size_t keygrid2_cells;
+    bool two_streams;   // VISSAT_ONE_STREAM=1 disables
     // optional per-view kernel timing of vs_views_to_dsm
     bool timing;
     std::vector<cudaEvent_t> ev_pool;   // 3 events per logged view: before A, between A and B, after B
