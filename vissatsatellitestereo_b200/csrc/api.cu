@@ -136,14 +136,17 @@ int vs_ctx_create(int device, vs_ctx** out) {
     ctx->scratch_doubles = 0;
     ctx->d_exact = nullptr;
     ctx->timing = false;
-    ctx->side_stream[0] = ctx->side_stream[1] = nullptr;
+    for (int i = 0; i < VS_MAX_STREAMS; ++i) {
+        ctx->side_stream[i] = nullptr;
+        ctx->join_event[i] = nullptr;
+        ctx->d_keygrid_extra[i] = nullptr;
+    }
     ctx->fork_event = nullptr;
-    ctx->join_event[0] = ctx->join_event[1] = nullptr;
-    ctx->d_keygrid2 = nullptr;
-    ctx->keygrid2_cells = 0;
+    ctx->keygrid_extra_cells = 0;
     {
-        const char* e1 = getenv("VISSAT_ONE_STREAM");
-        ctx->two_streams = !(e1 != nullptr && e1[0] == '1');
+        const char* e1 = getenv("VISSAT_STREAMS");
+        int n = e1 ? atoi(e1) : 4;
+        ctx->n_streams = n < 1 ? 1 : (n > VS_MAX_STREAMS ? VS_MAX_STREAMS : n);
     }
     {
         // The TMA-fed persistent variant of stage B (finalize_tma.cu) is bit-identical but measured slower than
@@ -163,12 +166,12 @@ int vs_ctx_destroy(vs_ctx* ctx) {
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     if (ctx->d_exact) cudaFree(ctx->d_exact);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < VS_MAX_STREAMS; ++i) {
         if (ctx->side_stream[i]) cudaStreamDestroy(ctx->side_stream[i]);
         if (ctx->join_event[i]) cudaEventDestroy(ctx->join_event[i]);
+        if (ctx->d_keygrid_extra[i]) cudaFree(ctx->d_keygrid_extra[i]);
     }
     if (ctx->fork_event) cudaEventDestroy(ctx->fork_event);
-    if (ctx->d_keygrid2) cudaFree(ctx->d_keygrid2);
     delete ctx;
     return VS_OK;
 }

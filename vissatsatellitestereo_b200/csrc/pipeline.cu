@@ -27,30 +27,35 @@ int vs_views_to_dsm(vs_ctx* ctx, int32_t n_views, const float* const* depth, con
             ctx->ev_pool.push_back(e);
         }
     }
-    // Two internal streams: view v runs on stream v & 1 with its own key grid, so stage A (FP64/XU/issue-bound) of one
+    // Internal streams: view v runs on stream v % NS with its own key grid, so stage A (FP64/XU/issue-bound) of one
     // view overlaps stage B (ALU-bound) of the previous one.  Fork from / join into the caller's stream with events.
-    const bool dual = ctx->two_streams && n_views >= 2;
+    const int NS = ctx->n_streams < n_views ? ctx->n_streams : n_views;
+    const bool dual = NS >= 2;
     if (dual) {
-        if (!ctx->side_stream[0]) {
-            for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < NS; ++i) {
+            if (!ctx->side_stream[i]) {
                 VS_CUDA(cudaStreamCreateWithFlags(&ctx->side_stream[i], cudaStreamNonBlocking));
                 VS_CUDA(cudaEventCreateWithFlags(&ctx->join_event[i], cudaEventDisableTiming));
             }
-            VS_CUDA(cudaEventCreateWithFlags(&ctx->fork_event, cudaEventDisableTiming));
         }
-        if (ctx->keygrid2_cells < (size_t)xs * ys) {
-            if (ctx->d_keygrid2) cudaFree(ctx->d_keygrid2);
-            ctx->d_keygrid2 = nullptr;
-            ctx->keygrid2_cells = 0;
-            VS_CUDA(cudaMalloc(&ctx->d_keygrid2, (size_t)xs * ys * sizeof(uint32_t)));
-            ctx->keygrid2_cells = (size_t)xs * ys;
+        if (!ctx->fork_event) VS_CUDA(cudaEventCreateWithFlags(&ctx->fork_event, cudaEventDisableTiming));
+        if (ctx->keygrid_extra_cells < (size_t)xs * ys) {
+            for (int i = 1; i < VS_MAX_STREAMS; ++i) {
+                if (ctx->d_keygrid_extra[i]) cudaFree(ctx->d_keygrid_extra[i]);
+                ctx->d_keygrid_extra[i] = nullptr;
+            }
+            ctx->keygrid_extra_cells = 0;
         }
+        for (int i = 1; i < NS; ++i)
+            if (!ctx->d_keygrid_extra[i]) VS_CUDA(cudaMalloc(&ctx->d_keygrid_extra[i], (size_t)xs * ys * sizeof(uint32_t)));
+        ctx->keygrid_extra_cells = (size_t)xs * ys;
         VS_CUDA(cudaEventRecord(ctx->fork_event, stream));
-        for (int i = 0; i < 2; ++i) VS_CUDA(cudaStreamWaitEvent(ctx->side_stream[i], ctx->fork_event, 0));
+        for (int i = 0; i < NS; ++i) VS_CUDA(cudaStreamWaitEvent(ctx->side_stream[i], ctx->fork_event, 0));
     }
     for (int v = 0; v < n_views; ++v) {
-        cudaStream_t st = dual ? ctx->side_stream[v & 1] : stream;
-        uint32_t* kg = (dual && (v & 1)) ? ctx->d_keygrid2 : keygrid;
+        const int si = dual ? v % NS : 0;
+        cudaStream_t st = dual ? ctx->side_stream[si] : stream;
+        uint32_t* kg = si ? ctx->d_keygrid_extra[si] : keygrid;
         int rc = vs_keygrid_clear(ctx, kg, (int64_t)xs * ys, 4, st);
         if (rc) return rc;
         if (ctx->timing) VS_CUDA(cudaEventRecord(ctx->ev_pool[ctx->ev_used + 0], st));
@@ -67,7 +72,7 @@ int vs_views_to_dsm(vs_ctx* ctx, int32_t n_views, const float* const* depth, con
         }
     }
     if (dual) {
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < NS; ++i) {
             VS_CUDA(cudaEventRecord(ctx->join_event[i], ctx->side_stream[i]));
             VS_CUDA(cudaStreamWaitEvent(stream, ctx->join_event[i], 0));
         }
