@@ -149,6 +149,10 @@ int vs_views_to_dsm(vs_ctx* ctx, int32_t n_views, const float* const* depth, con
                     const double* inv_proj_mats, uint32_t* keygrid, float* dsm_stack, int64_t plane_stride,
                     int simd_lanes, uint64_t* nan_counts, uint64_t* stats, void* stream);
 
+/* Number of internal streams vs_views_to_dsm spreads consecutive views over (1..4, default 4 or $VISSAT_STREAMS).
+ * With more than one, stage A of one view overlaps stage B of another (they are bound by different pipes). */
+int vs_set_streams(vs_ctx* ctx, int n_streams);
+
 /* Per-kernel device timing of vs_views_to_dsm (CUDA events recorded on the launching stream around stage A and stage
  * B of every view).  vs_set_timing(ctx, 1) enables it and resets the log; vs_get_timing synchronises the events and
  * returns up to `max` (stage A ms, stage B ms) pairs in call order; *n_out = number of views logged. */

@@ -55,6 +55,7 @@ SIGNATURES = {
     'vs_grid_finalize64': (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, C.c_int, _vp]),
     'vs_views_to_dsm': (C.c_int, [_vp, _i32, C.POINTER(_vp), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_dbl), _vp, _vp,
                                   _i64, C.c_int, _vp, _vp, _vp]),
+    'vs_set_streams': (C.c_int, [_vp, C.c_int]),
     'vs_set_timing': (C.c_int, [_vp, C.c_int]),
     'vs_get_timing': (C.c_int, [_vp, _i32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(_i32)]),
     'vs_fuse_views': (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),

@@ -80,6 +80,13 @@ int vs_views_to_dsm(vs_ctx* ctx, int32_t n_views, const float* const* depth, con
     return VS_OK;
 }
 
+int vs_set_streams(vs_ctx* ctx, int n_streams) {
+    VS_REQUIRE(ctx != nullptr, "vs_set_streams: NULL context");
+    VS_REQUIRE(n_streams >= 1 && n_streams <= VS_MAX_STREAMS, "vs_set_streams: n_streams must be 1..4");
+    ctx->n_streams = n_streams;
+    return VS_OK;
+}
+
 int vs_set_timing(vs_ctx* ctx, int enable) {
     VS_REQUIRE(ctx != nullptr, "vs_set_timing: NULL context");
     ctx->timing = enable != 0;

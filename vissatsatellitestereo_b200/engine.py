@@ -125,6 +125,9 @@ class DsmEngine:
                                   _ptr(self.keygrid), _ptr(out), stack.stride(0), self.simd_lanes,
                                   _ptr(count_nan), C.c_void_p(0), _stream(self.device)), 'vs_views_to_dsm')
 
+    def set_streams(self, n):
+        check(lib.vs_set_streams(self.ctx.handle, int(n)), 'vs_set_streams')
+
     def set_timing(self, enable):
         check(lib.vs_set_timing(self.ctx.handle, 1 if enable else 0), 'vs_set_timing')
 
