@@ -249,16 +249,18 @@ __device__ __forceinline__ uint32_t group_max(uint32_t v, unsigned mask) {
     return v;
 }
 
-// number of keys < T in this lane's sorted run (NVL keys, stride LANES)
+// Runs are stored padded with 0xffffffff up to NVLP = the power of two above NVL, so the branch-free lower bound
+// needs no range checks.
+template <int NVL> struct RunPad { static constexpr int value = NVL < 8 ? 8 : NVL < 16 ? 16 : NVL < 32 ? 32 : NVL < 64 ? 64 : 128; };
+
+// number of keys < T in this lane's sorted run (stride LANES)
 template <int LANES, int NVL>
 __device__ __forceinline__ int run_lower_bound(const uint32_t* __restrict__ run, uint32_t T) {
-    constexpr int P = NVL >= 128 ? 128 : NVL >= 64 ? 64 : NVL >= 32 ? 32 : NVL >= 16 ? 16 : 8;
+    constexpr int P = RunPad<NVL>::value;
     int lb = 0;
 #pragma unroll
-    for (int step = P; step >= 1; step >>= 1) {
-        const int idx = lb + step;
-        if (idx <= NVL && run[(idx - 1) * LANES] < T) lb = idx;
-    }
+    for (int step = P / 2; step >= 1; step >>= 1)
+        if (run[(lb + step - 1) * LANES] < T) lb += step;
     return lb;
 }
 
@@ -333,6 +335,8 @@ k_fuse_large(const float* __restrict__ views, int64_t plane_stride, int V, int64
     SortNet<NVL>::sort(s);
 #pragma unroll
     for (int i = 0; i < NVL; ++i) run[i * LANES] = vs_key32(s[i]);
+#pragma unroll
+    for (int i = NVL; i < RunPad<NVL>::value; ++i) run[i * LANES] = 0xffffffffu;   // pads: never below any threshold
     __syncwarp(gmask);
 
     // 3. median
@@ -385,18 +389,31 @@ k_fuse_large(const float* __restrict__ views, int64_t plane_stride, int V, int64
             float leaf;
             if (n < 8) {
                 leaf = 0.0f;
-                for (int i = 0; i < n; ++i) leaf = __fadd_rn(leaf, y(off + i));   // every lane computes the same value
+                for (int i = 0; i < n; ++i) {   // every lane computes the same value
+                    leaf = __fadd_rn(leaf, y(off + i));
+                    if (lane == 0) cnt += y.kept(off + i);
+                }
             } else {
                 float r[ACC];
 #pragma unroll
                 for (int m = 0; m < ACC; ++m) r[m] = 0.0f;
                 const int nfull = n - (n & 7);
-                if (acc_lane) {
+                if (acc_lane) {   // every view index of the leaf's full blocks is visited exactly once: count here too
 #pragma unroll
-                    for (int m = 0; m < ACC; ++m) r[m] = y(off + lane + m * AL);
-                    for (int i = 8; i < nfull; i += 8) {
-#pragma unroll
-                        for (int m = 0; m < ACC; ++m) r[m] = __fadd_rn(r[m], y(off + i + lane + m * AL));
+                    for (int m = 0; m < ACC; ++m) {
+                        const float* q = y.p + (int64_t)(off + lane + m * AL) * y.stride;
+                        const int64_t step8 = 8 * y.stride;
+                        float t = __ldg(q);
+                        bool keep = (t == t) && !(fabsf(__fsub_rn(t, y.med)) > y.mad);
+                        r[m] = keep ? t : 0.0f;
+                        cnt += keep;
+                        for (int i = 8; i < nfull; i += 8) {
+                            q += step8;
+                            t = __ldg(q);
+                            keep = (t == t) && !(fabsf(__fsub_rn(t, y.med)) > y.mad);
+                            r[m] = __fadd_rn(r[m], keep ? t : 0.0f);
+                            cnt += keep;
+                        }
                     }
                 }
                 // gather r[0..7] (accumulator a lives in lane a % AL, slot a / AL) and combine as numpy does:
@@ -406,7 +423,10 @@ k_fuse_large(const float* __restrict__ views, int64_t plane_stride, int V, int64
                 for (int a = 0; a < 8; ++a) a8[a] = __shfl_sync(gmask, r[a / AL], a % AL, LANES);
                 leaf = __fadd_rn(__fadd_rn(__fadd_rn(a8[0], a8[1]), __fadd_rn(a8[2], a8[3])),
                                  __fadd_rn(__fadd_rn(a8[4], a8[5]), __fadd_rn(a8[6], a8[7])));
-                for (int i = nfull; i < n; ++i) leaf = __fadd_rn(leaf, y(off + i));
+                for (int i = nfull; i < n; ++i) {
+                    leaf = __fadd_rn(leaf, y(off + i));
+                    if (lane == 0) cnt += y.kept(off + i);
+                }
             }
             // ---- combine with finished left siblings
             float val = leaf;
@@ -422,7 +442,6 @@ k_fuse_large(const float* __restrict__ views, int64_t plane_stride, int V, int64
         }
         total = stack_val[0];
     }
-    for (int v = lane; v < V; v += LANES) cnt += y.kept(v);
     cnt = group_sum<LANES>(cnt, gmask);
     if (lane == 0) out[cell] = __fdiv_rn(total, (float)cnt);
 }
@@ -449,7 +468,7 @@ template <int LANES, int NVL>
 int launch_large_t(vs_ctx* ctx, const float* views, int64_t plane_stride, int V, int64_t n_cells, float* out,
                    cudaStream_t stream) {
     constexpr int CELLS = kLargeThreads / LANES;
-    int VS = LANES * NVL;
+    int VS = LANES * RunPad<NVL>::value;
     VS += (9 - (VS & 31) + 32) & 31;  // row stride = 9 (mod 32): conflict-free tile stores, few conflicts on the runs
     const size_t smem = (size_t)CELLS * VS * sizeof(uint32_t);
     VS_CUDA(cudaFuncSetAttribute(k_fuse_large<LANES, NVL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -115,7 +115,8 @@ __host__ __device__ __forceinline__ uint32_t vs_key32(float f) {
 #else
     union { float f; uint32_t u; } c; c.f = f; uint32_t b = c.u;
 #endif
-    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+    // negative: invert all bits; non-negative: set the top bit.  Branch-free: b ^ (sign_mask | 0x80000000)
+    return b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u);
 }
 __device__ __forceinline__ float vs_unkey32(uint32_t k) {
     // top bit set: clear it; top bit clear: invert everything.  Branch-free: k ^ (0x80000000 | ~sign_mask).
