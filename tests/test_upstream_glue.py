@@ -1,0 +1,106 @@
+"""host glue either side of the path -- write_aoi (stereo_pipeline.py:185-226) and the
+inv_proj_mats derivation (reparam_depth.py:117-141).  CPU only."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+from oracle import geodesy, pipeline as op
+from vissatsatellitestereo_b200 import synthetic as S
+
+
+def _rotation_to_quaternion(R):
+    w = math.sqrt(max(0.0, 1 + R[0, 0] + R[1, 1] + R[2, 2])) / 2
+    x = math.copysign(math.sqrt(max(0.0, 1 + R[0, 0] - R[1, 1] - R[2, 2])) / 2, R[2, 1] - R[1, 2])
+    y = math.copysign(math.sqrt(max(0.0, 1 - R[0, 0] + R[1, 1] - R[2, 2])) / 2, R[0, 2] - R[2, 0])
+    z = math.copysign(math.sqrt(max(0.0, 1 - R[0, 0] - R[1, 1] + R[2, 2])) / 2, R[1, 0] - R[0, 1])
+    return w, x, y, z
+
+
+def test_write_aoi_matches_explorer_config(tmp_path):
+    """aoi_config/MVS3DM_Explorer.json:4-11 bounding box; corners cross-checked against the PROJ inverse restatement."""
+    from vissatsatellitestereo_b200.stereo_pipeline import write_aoi, utm_to_latlon
+    config = {'work_dir': str(tmp_path), 'alt_min': -30.0, 'alt_max': 120.0,
+              'bounding_box': {'zone_number': 21, 'hemisphere': 'S', 'ul_easting': 354052.3651180889,
+                               'ul_northing': 6182702.10540914, 'width': 712.0, 'height': 652.0}}
+    aoi = write_aoi(config)
+    with open(os.path.join(str(tmp_path), 'aoi.json')) as fp:
+        assert json.load(fp) == aoi
+    assert list(aoi.keys()) == ['zone_number', 'hemisphere', 'ul_easting', 'ul_northing', 'lr_easting', 'lr_northing',
+                                'width', 'height', 'lat_min', 'lat_max', 'lon_min', 'lon_max', 'alt_min', 'alt_max']
+    assert aoi['lr_easting'] == 354052.3651180889 + 712.0 and aoi['lr_northing'] == 6182702.10540914 - 652.0
+    # UL corner of the Explorer AOI through the (independent) PROJ inverse: -34.486961674 / -58.589466115
+    lat, lon = utm_to_latlon(354052.3651180889, 6182702.10540914, 21, False)
+    assert abs(lat - -34.486961674) < 5e-8 and abs(lon - -58.589466115) < 5e-8
+    for e, n in ((aoi['ul_easting'], aoi['ul_northing']), (aoi['lr_easting'], aoi['lr_northing'])):
+        plat, plon = geodesy.utm_inverse(e, n, 21, True)
+        lat, lon = utm_to_latlon(e, n, 21, False)
+        assert abs(lat - plat) < 5e-8 and abs(lon - plon) < 5e-8
+    assert aoi['lat_min'] < aoi['lat_max'] < 0 and aoi['lon_min'] < aoi['lon_max'] < 0
+    # northern hemisphere / other zone
+    lat, lon = utm_to_latlon(395201.3103816, 5673135.2407718, 32, True)
+    assert abs(lat - 51.2) < 5e-8 and abs(lon - 7.5) < 5e-8
+
+
+def test_inv_proj_mats_from_camera_dict(tmp_path):
+    """P4 = [K[R|t]; last_row], M = inv(P4): rebuilds the matrices the synthetic scenes (and the adapted COLMAP) use."""
+    from vissatsatellitestereo_b200 import reparam_depth as RD
+    from vissatsatellitestereo_b200.aggregate_2p5d_util import load_inv_proj_mats
+    cfg = S.scaled(S.CONFIGS['C1'], views=4, depth=64, grid=32, name='glue')
+    camera_dict, last_rows, want = {}, {}, {}
+    for v in range(4):
+        M, P4 = S.make_camera(cfg, v, cfg.alt_min)
+        K = np.array([[P4[2, :3] @ P4[2, :3]]])            # |r3| = 1 for a rotation row
+        assert abs(K[0, 0] - 1) < 1e-12
+        R3 = P4[2, :3]
+        # decompose P3 = K [R|t] (K upper triangular with K22 = 1, zero skew here)
+        f = np.linalg.norm(np.cross(P4[0, :3], R3))
+        cx, cy = P4[0, :3] @ R3, P4[1, :3] @ R3
+        R = np.vstack(((P4[0, :3] - cx * R3) / f, (P4[1, :3] - cy * R3) / f, R3))
+        Kmat = np.array([[f, 0, cx], [0, f, cy], [0, 0, 1.0]])
+        t = np.linalg.solve(Kmat, P4[:3, 3])
+        name = S.view_name(v)
+        camera_dict[name] = (cfg.width, cfg.height, f, f, cx, cy, 0.0) + _rotation_to_quaternion(R) + tuple(t)
+        last_rows[name] = P4[3]
+        want[name] = M
+        assert np.allclose(RD.quaternion_to_rotation(*_rotation_to_quaternion(R)), R, atol=1e-12)
+    # non-unit quaternions are normalised (pyquaternion does the same)
+    assert np.allclose(RD.quaternion_to_rotation(2, 0, 0, 0), np.eye(3))
+    with open(str(tmp_path / 'last_rows.txt'), 'w') as fp:                # reparam_depth.py:171-174 format
+        for name in sorted(last_rows):
+            vec = last_rows[name]
+            fp.write('{} {} {} {} {}\n'.format(name, vec[0], vec[1], vec[2], vec[3]))
+    path = RD.ensure_inv_proj_mats(str(tmp_path), camera_dict)
+    got = load_inv_proj_mats(str(tmp_path))
+    assert sorted(got) == sorted(want)
+    pix = np.array([[10.0, 20.0, 1.0, 597990.0]]).T
+    for name in want:
+        a, b = got[name] @ pix, want[name] @ pix
+        assert np.allclose(a[:3] / a[3], b[:3] / b[3], rtol=0, atol=1e-6)       # same ENU point to a micrometre
+    # an existing file is left alone
+    os.utime(path, (1, 1))
+    RD.ensure_inv_proj_mats(str(tmp_path), camera_dict)
+    assert os.path.getmtime(path) == 1
+
+
+def test_pipeline_rejects_out_of_scope_steps(tmp_path):
+    from vissatsatellitestereo_b200.stereo_pipeline import StereoPipeline
+    cfgfile = str(tmp_path / 'c.json')
+    config = {'work_dir': str(tmp_path / 'w'), 'alt_min': -30.0, 'alt_max': 120.0,
+              'bounding_box': {'zone_number': 21, 'hemisphere': 'S', 'ul_easting': 354052.3651180889,
+                               'ul_northing': 6182702.10540914, 'width': 100.0, 'height': 100.0},
+              'steps_to_run': {'clean_data': False, 'colmap_mvs': True, 'aggregate_2p5d': False, 'aggregate_3d': False}}
+    with open(cfgfile, 'w') as fp:
+        json.dump(config, fp)
+    os.makedirs(config['work_dir'])
+    with pytest.raises(NotImplementedError):
+        StereoPipeline(cfgfile).run()
+    config['steps_to_run']['colmap_mvs'] = False
+    with open(cfgfile, 'w') as fp:
+        json.dump(config, fp)
+    StereoPipeline(cfgfile).run()
+    assert os.path.exists(os.path.join(config['work_dir'], 'aoi.json'))
+    with open(os.path.join(config['work_dir'], 'runtime.txt')) as fp:
+        assert 'aggregate_2p5d, skipped' in fp.read()
