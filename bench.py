@@ -235,17 +235,25 @@ def run_b200_arm(args, cfg):
     n_waves = 5 if world > 1 else 1
     wave_edges = [round(i * V / n_waves) for i in range(n_waves + 1)]
 
-    xch = D.WaveExchanger(stack, view_counts) if (world > 1 and cfg.fuse) else None     # buffers allocated once
+    # multi-GPU transpose (views -> row bands): stage B stores the bands into the peers' stacks itself (CUDA-IPC peer
+    # memory over NVLink); VISSAT_EXCHANGE=nccl selects the NCCL send/recv waves instead.  Buffers are allocated once.
+    xch, xch_kind = (D.make_exchange(eng, stack, view_counts, prefer=os.environ.get('VISSAT_EXCHANGE', 'peer'))
+                     if (world > 1 and cfg.fuse) else (None, 'none'))
+    peer = xch_kind == 'peer-store'
 
     def step(record):
         if record:
             ab0, ab1 = ev(), ev()
             ab0.record()
-        for w in range(n_waves):
-            a, b = wave_edges[w], wave_edges[w + 1]
-            eng.views_to_dsm(depths[a:b], mats[a:b], stack, first=a)     # one library call per wave (stages A + B)
-            if xch is not None:
-                xch.send_wave(a, b)                                      # overlaps stages A/B of the next wave
+        if peer:
+            xch.begin_step()
+            eng.views_to_dsm(depths, mats, stack)                        # stage B also writes the peers' row bands
+        else:
+            for w in range(n_waves):
+                a, b = wave_edges[w], wave_edges[w + 1]
+                eng.views_to_dsm(depths[a:b], mats[a:b], stack, first=a)     # one library call per wave (stages A + B)
+                if xch is not None:
+                    xch.send_wave(a, b)                                      # overlaps stages A/B of the next wave
         if record:
             ab1.record()
             ab_events.append((ab0, ab1))
@@ -384,6 +392,8 @@ def run_b200_arm(args, cfg):
         if cfg.fuse and world == 1:
             assert np.array_equal(host_fused.numpy(), fused.cpu().numpy(), equal_nan=True), 'e2e result differs'
 
+    if peer:
+        xch.close()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -444,6 +454,11 @@ def run_b200_arm(args, cfg):
             'pipeline': {'algorithmic_bytes_per_step': b_alg, 'achieved_gbs': pipeline_gbs,
                          'frac_of_hbm_peak': pipeline_gbs / (peak * world)},
             'fit': eng.fit}
+    if world > 1:
+        line['config']['exchange'] = {'peer-store': 'stage-B kernel stores row bands into the peers\' stacks '
+                                                    '(CUDA IPC peer memory over NVLink) + 1-element all-reduce barrier',
+                                      'nccl-waves': 'NCCL grouped send/recv in 5 waves overlapped with stages A/B',
+                                      'none': 'none (no fusion)'}[xch_kind]
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

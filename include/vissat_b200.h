@@ -159,6 +159,45 @@ int vs_set_streams(vs_ctx* ctx, int n_streams);
 int vs_set_timing(vs_ctx* ctx, int enable);
 int vs_get_timing(vs_ctx* ctx, int32_t max, float* stage_a_ms, float* stage_b_ms, int32_t* n_out);
 
+/* ---- multi-GPU: stage B writes the row-band exchange itself (peer stores over NVLink) ----------------------------
+ * views are sharded over ranks (one process per GPU), fusion is sharded by grid row bands, and the
+ * transpose between the two layouts replaces the file-system hand-off of aggregate_2p5d.py:57-66.  Instead of a
+ * collective after stage B, the stage-B kernel of vs_views_to_dsm stores every output row, besides the local per-view
+ * DSM, straight into the (view, row-band) stack of the rank that fuses that row -- and into the 1-row halo of the
+ * neighbouring bands for the final 3x3 blur -- through peer-mapped device memory.  The transfer overlaps the kernel
+ * tile by tile; no pack/copy kernels, no second pass over the data.
+ *
+ * vs_peer_alloc / vs_peer_open: device memory that another process can map (cudaMalloc + CUDA IPC handle; the 64
+ * handle bytes travel through the host language's own channel, e.g. torch.distributed.all_gather_object).
+ * vs_peer_close unmaps a pointer obtained from vs_peer_open; vs_peer_free releases one from vs_peer_alloc.
+ */
+#define VS_MAX_RANKS 16
+#define VS_IPC_HANDLE_BYTES 64
+int vs_peer_alloc(vs_ctx* ctx, uint64_t bytes, void** dptr, uint8_t* handle64);
+int vs_peer_open(vs_ctx* ctx, const uint8_t* handle64, void** dptr);
+int vs_peer_close(vs_ctx* ctx, void* dptr);
+int vs_peer_free(vs_ctx* ctx, void* dptr);
+
+/* Row bands follow numpy.array_split(arange(ysize), n_ranks) (aggregate_2p5d_util.py:109-122 splits its work list
+ * the same way): the first ysize % n_ranks bands have one row more.  band_stack[j] is rank j's float32 array
+ * (n_views_total, rows_j + halo rows present, xsize): plane g holds the rows [max(r0_j - halo, 0),
+ * min(r1_j + halo, ysize)) of global view g.  A plane of vs_views_to_dsm's dsm_stack at local_stack + i*plane_stride
+ * is global view view0 + i.  The caller orders the ranks' use of the stacks (all stage-B kernels of a step complete
+ * on every rank -- a stream-ordered barrier such as a 1-element all-reduce -- before any rank fuses its stack, and a
+ * stack is not rewritten before its owner has fused it: alternate between two stacks). */
+typedef struct vs_exchange {
+    int32_t n_ranks;
+    int32_t rank;
+    int32_t halo;              /* rows of neighbouring bands kept on each side (1 for the 3x3 blur) */
+    int32_t reserved;
+    int64_t view0;             /* global index of this rank's first view */
+    int64_t n_views_total;
+    const float* local_stack;  /* base of the local per-view DSM stack (plane 0) */
+    float* band_stack[VS_MAX_RANKS];
+} vs_exchange;
+/* Enable (ex != NULL; the struct is copied) or disable (ex == NULL) the peer stores of vs_views_to_dsm. */
+int vs_set_exchange(vs_ctx* ctx, const vs_exchange* ex);
+
 /* ---- stage C: cross-view fusion --------------------------------------------------------------------------
  * Replaces aggregate_2p5d.py:65-78: per cell over V views (in the given order = sorted file order):
  * count filter (<= 2 measurements -> NaN), np.nanmedian, MAD = nanmedian(|x - med|), reject |x - med| > MAD,

@@ -34,6 +34,16 @@ class vs_fit_info(C.Structure):
                 ('box_center', C.c_double * 3), ('box_half', C.c_double * 3)]
 
 
+VS_MAX_RANKS = 16
+VS_IPC_HANDLE_BYTES = 64
+
+
+class vs_exchange(C.Structure):
+    _fields_ = [('n_ranks', C.c_int32), ('rank', C.c_int32), ('halo', C.c_int32), ('reserved', C.c_int32),
+                ('view0', C.c_int64), ('n_views_total', C.c_int64), ('local_stack', C.c_void_p),
+                ('band_stack', C.c_void_p * VS_MAX_RANKS)]
+
+
 _vp = C.c_void_p
 _i32 = C.c_int32
 _i64 = C.c_int64
@@ -66,6 +76,11 @@ SIGNATURES = {
     'vs_utm_to_geodetic': (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp]),
     'vs_enu_to_utm': (C.c_int, [_vp, _vp, _vp, _vp, _i64, _dbl, _dbl, _dbl, _i32, _i32, _vp, _vp, _vp, _vp]),
     'vs_launch_count': (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
+    'vs_peer_alloc': (C.c_int, [_vp, C.c_uint64, C.POINTER(_vp), C.POINTER(C.c_uint8)]),
+    'vs_peer_open': (C.c_int, [_vp, C.POINTER(C.c_uint8), C.POINTER(_vp)]),
+    'vs_peer_close': (C.c_int, [_vp, _vp]),
+    'vs_peer_free': (C.c_int, [_vp, _vp]),
+    'vs_set_exchange': (C.c_int, [_vp, C.POINTER(vs_exchange)]),
 }
 
 

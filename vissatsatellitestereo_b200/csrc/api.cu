@@ -136,6 +136,8 @@ int vs_ctx_create(int device, vs_ctx** out) {
     ctx->scratch_doubles = 0;
     ctx->d_exact = nullptr;
     ctx->timing = false;
+    ctx->xch_on = false;
+    memset(&ctx->xch, 0, sizeof(ctx->xch));
     for (int i = 0; i < VS_MAX_STREAMS; ++i) {
         ctx->side_stream[i] = nullptr;
         ctx->join_event[i] = nullptr;

@@ -19,15 +19,19 @@ using namespace vsfin;
 namespace {
 
 // all-empty tile: every output is NaN (hole fill and blur of nothing)
-template <typename T>
+template <typename T, typename Sink>
 __device__ __forceinline__ void write_nan_tile(float* __restrict__ blur_out, T* __restrict__ filled_out, int ty0, int tx0,
-                                               int H, int W, unsigned long long* __restrict__ nan_count) {
+                                               int H, int W, unsigned long long* __restrict__ nan_count,
+                                               const Sink& sink) {
     unsigned n = 0;
     for (int i = threadIdx.x; i < TW * TH; i += kThreads) {
         const int r = i / TW, c = i - r * TW;
         const int gy = ty0 + r, gx = tx0 + c;
         if (gy < H && gx < W) {
-            if (blur_out != nullptr) blur_out[(size_t)gy * W + gx] = CUDART_NAN_F;
+            if (blur_out != nullptr) {
+                blur_out[(size_t)gy * W + gx] = CUDART_NAN_F;
+                sink.store1(gy, gx, W, CUDART_NAN_F);
+            }
             if (filled_out != nullptr) filled_out[(size_t)gy * W + gx] = (T)CUDART_NAN;
             ++n;
         }
@@ -35,10 +39,11 @@ __device__ __forceinline__ void write_nan_tile(float* __restrict__ blur_out, T* 
     if (blur_out != nullptr) block_count_flush(n, nan_count);
 }
 
-template <typename Key>
+template <typename Key, typename Sink>
 __global__ void __launch_bounds__(kThreads)
 k_grid_finalize(const Key* __restrict__ keygrid, int W, int H, typename KeyTraits<Key>::value_t* __restrict__ filled_out,
-                float* __restrict__ blur_out, int simd_cols, unsigned long long* __restrict__ nan_count) {
+                float* __restrict__ blur_out, int simd_cols, unsigned long long* __restrict__ nan_count,
+                const __grid_constant__ Sink sink) {
     typedef typename KeyTraits<Key>::value_t T;
     constexpr bool kSameTile = sizeof(T) == sizeof(float);   // float32 keys: one tile serves fill and blur
     __shared__ __align__(16) T s_raw[TR * TS];              // decoded keys; holes are patched in place after phase 2
@@ -81,7 +86,7 @@ k_grid_finalize(const Key* __restrict__ keygrid, int W, int H, typename KeyTrait
 #pragma unroll
             for (int q = 0; q < NV4; ++q) nz |= kv[q].x | kv[q].y | kv[q].z | kv[q].w;
             if (!__syncthreads_or(nz != 0)) {
-                write_nan_tile(blur_out, filled_out, ty0, tx0, H, W, nan_count);
+                write_nan_tile(blur_out, filled_out, ty0, tx0, H, W, nan_count, sink);
                 return;
             }
         }
@@ -141,7 +146,7 @@ k_grid_finalize(const Key* __restrict__ keygrid, int W, int H, typename KeyTrait
 #pragma unroll
                 for (int part = 0; part < 3; ++part) nz |= (keys[it][part] != 0);
             if (!__syncthreads_or(nz)) {
-                write_nan_tile(blur_out, filled_out, ty0, tx0, H, W, nan_count);
+                write_nan_tile(blur_out, filled_out, ty0, tx0, H, W, nan_count, sink);
                 return;
             }
         }
@@ -218,7 +223,7 @@ k_grid_finalize(const Key* __restrict__ keygrid, int W, int H, typename KeyTrait
     // 3. cv2.medianBlur(., 3) with replicated borders
     replicate_border(s_fill, ty0, tx0, H, W);
     __syncthreads();
-    const unsigned n_nan = blur_tile(s_fill, ty0, tx0, H, W, H, s_has_nan != 0, simd_cols != 0, blur_out, 0);
+    const unsigned n_nan = blur_tile(s_fill, ty0, tx0, H, W, H, s_has_nan != 0, simd_cols != 0, blur_out, 0, sink);
     block_count_flush(n_nan, nan_count);
 }
 
@@ -308,6 +313,21 @@ k_median3x3(const float* __restrict__ in, int in_row0, int H, int W, int row_beg
 
 }  // namespace
 
+// Stage B of one view with the peer stores of the multi-GPU exchange (called by vs_views_to_dsm, pipeline.cu).
+int vs_grid_finalize_peer(vs_ctx* ctx, const uint32_t* keygrid, int xsize, int ysize, float* dsm_out, int simd_lanes,
+                          uint64_t* nan_count, const VsPeerPlan& plan, cudaStream_t stream) {
+    if (nan_count) VS_CUDA(cudaMemsetAsync(nan_count, 0, sizeof(uint64_t), stream));
+    PeerSink sink;
+    sink.p = plan;
+    dim3 grid((xsize + TW - 1) / TW, (ysize + TH - 1) / TH);
+    k_grid_finalize<uint32_t, PeerSink><<<grid, kThreads, 0, stream>>>(keygrid, xsize, ysize, nullptr, dsm_out,
+                                                                      simd_cols_for(xsize, simd_lanes),
+                                                                      reinterpret_cast<unsigned long long*>(nan_count),
+                                                                      sink);
+    VS_CHECK_LAUNCH(ctx, "k_grid_finalize<u32, peer>");
+    return VS_OK;
+}
+
 int vs_finalize_tma_try(vs_ctx* ctx, bool keys, const void* in, int in_rows, int in_row0, int W, int H, int row_begin,
                         int row_end, float* out, int simd_cols, unsigned long long* nan_count, cudaStream_t stream);
 
@@ -331,9 +351,10 @@ int vs_grid_finalize(vs_ctx* ctx, const uint32_t* keygrid, int32_t xsize, int32_
         if (r > 0) return VS_OK;
     }
     dim3 grid((xsize + TW - 1) / TW, (ysize + TH - 1) / TH);
-    k_grid_finalize<uint32_t><<<grid, kThreads, 0, stream>>>(keygrid, xsize, ysize, nullptr, dsm_out,
-                                                            simd_cols_for(xsize, simd_lanes),
-                                                            reinterpret_cast<unsigned long long*>(nan_count));
+    k_grid_finalize<uint32_t, NoSink><<<grid, kThreads, 0, stream>>>(keygrid, xsize, ysize, nullptr, dsm_out,
+                                                                    simd_cols_for(xsize, simd_lanes),
+                                                                    reinterpret_cast<unsigned long long*>(nan_count),
+                                                                    NoSink());
     VS_CHECK_LAUNCH(ctx, "k_grid_finalize<u32>");
     return VS_OK;
 }
@@ -348,9 +369,9 @@ int vs_grid_finalize64(vs_ctx* ctx, const uint64_t* keygrid64, int32_t xsize, in
     if (!guard.ok) return vs_cuda_fail(cudaGetLastError(), "cudaSetDevice");
     cudaStream_t stream = (cudaStream_t)stream_;
     dim3 grid((xsize + TW - 1) / TW, (ysize + TH - 1) / TH);
-    k_grid_finalize<unsigned long long><<<grid, kThreads, 0, stream>>>(
+    k_grid_finalize<unsigned long long, NoSink><<<grid, kThreads, 0, stream>>>(
         reinterpret_cast<const unsigned long long*>(keygrid64), xsize, ysize, filled64, blurred32,
-        simd_cols_for(xsize, simd_lanes), nullptr);
+        simd_cols_for(xsize, simd_lanes), nullptr, NoSink());
     VS_CHECK_LAUNCH(ctx, "k_grid_finalize<u64>");
     return VS_OK;
 }

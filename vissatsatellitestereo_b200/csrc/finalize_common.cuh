@@ -73,12 +73,57 @@ __device__ __forceinline__ float median9_exact(const float* r0, const float* r1,
                 : vs_median9_net<false>(r0[0], r0[1], r0[2], r1[0], r1[1], r1[2], r2[0], r2[1], r2[2]);
 }
 
+// ---- output sinks ----------------------------------------------------------------------------------------------
+// Besides the caller's array, stage B can store every output row into the row-band stacks of the ranks that fuse it
+// (multi-GPU exchange through peer-mapped memory).  NoSink compiles to nothing.
+struct NoSink {
+    __device__ __forceinline__ void store4(int, int, int, const float4&) const {}
+    __device__ __forceinline__ void store1(int, int, int, float) const {}
+};
+struct PeerSink {
+    VsPeerPlan p;
+    // band j of row y: row0[j] <= y < row0[j+1].  Bands are near-uniform (numpy.array_split), so y*n/H is at most
+    // one band off; the two loops make it exact (and step over empty bands when H < n).
+    __device__ __forceinline__ int band_of(int y) const {
+        int j = min((int)__umulhi((unsigned)y, p.inv), p.n - 1);
+        while (y < p.row0[j]) --j;
+        while (y >= p.row0[j + 1]) ++j;
+        return j;
+    }
+    __device__ __forceinline__ float* at(int j, int y, int x, int W) const {
+        const int h0 = max(p.row0[j] - p.halo, 0);
+        return p.plane[j] + (size_t)(y - h0) * W + x;
+    }
+    template <typename F>
+    __device__ __forceinline__ void each_dest(int y, F f) const {
+        const int j = band_of(y);
+        f(j);
+        // the first `halo` rows of band j are the lower halo of band j-1, the last ones the upper halo of band j+1
+        if (j > 0 && y - p.row0[j] < p.halo && p.row0[j] > p.row0[j - 1]) f(j - 1);
+        if (j + 1 < p.n && p.row0[j + 1] - y <= p.halo && p.row0[j + 2] > p.row0[j + 1]) f(j + 1);
+    }
+    __device__ __forceinline__ void store4(int y, int x, int W, const float4& v) const {
+        each_dest(y, [&](int j) {
+            float* d = at(j, y, x, W);
+            if ((reinterpret_cast<uintptr_t>(d) & 15) == 0) {
+                *reinterpret_cast<float4*>(d) = v;
+            } else {   // odd row pitch
+                d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+            }
+        });
+    }
+    __device__ __forceinline__ void store1(int y, int x, int W, float v) const {
+        each_dest(y, [&](int j) { *at(j, y, x, W) = v; });
+    }
+};
+
 // Blur phase shared by K2 and K4.  s_fill: TR x TS tile; element (r, OFF + c) is grid cell (ty0 - 2 + r, tx0 - 2 + c).
 // Rows/columns within the 1-cell halo must be final (hole-filled) and, outside the grid, replicated from the
 // nearest inside cell.  Writes out[(gy - out_row0) * W + gx] for gy in [ty0, min(ty0 + TH, row_limit)).
+template <typename Sink = NoSink>
 __device__ __forceinline__ unsigned blur_tile(const float* __restrict__ s_fill, int ty0, int tx0, int H, int W,
                                               int row_limit, bool tile_has_nan, bool simd_cols,
-                                              float* __restrict__ out, int out_row0) {
+                                              float* __restrict__ out, int out_row0, const Sink& sink = Sink()) {
     const int tid = threadIdx.x;
     unsigned n_nan = 0;
     if (H == 1 || W == 1) {  // OpenCV's 1-D special case (block-uniform): 3-tap median along the line
@@ -89,6 +134,7 @@ __device__ __forceinline__ unsigned blur_tile(const float* __restrict__ s_fill, 
                 const float* p = s_fill + (r + 2) * TS + (OFF + c + 2);
                 const float m = (H == 1) ? vs_median3_line(p[-1], p[0], p[1]) : vs_median3_line(p[-TS], p[0], p[TS]);
                 out[(size_t)(gy - out_row0) * W + gx] = m;
+                sink.store1(gy, gx, W, m);
                 n_nan += (m != m);
             }
         }
@@ -136,7 +182,9 @@ __device__ __forceinline__ unsigned blur_tile(const float* __restrict__ s_fill, 
         if (y_g < row_limit) {
             float* o = out + (size_t)(y_g - out_row0) * W + gx;
             if (gx + 3 < W && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-                *reinterpret_cast<float4*>(o) = make_float4(res[j][0], res[j][1], res[j][2], res[j][3]);
+                const float4 v4 = make_float4(res[j][0], res[j][1], res[j][2], res[j][3]);
+                *reinterpret_cast<float4*>(o) = v4;
+                sink.store4(y_g, gx, W, v4);
 #pragma unroll
                 for (int x = 0; x < 4; ++x) n_nan += (res[j][x] != res[j][x]);
             } else {
@@ -144,6 +192,7 @@ __device__ __forceinline__ unsigned blur_tile(const float* __restrict__ s_fill, 
                 for (int x = 0; x < 4; ++x)
                     if (gx + x < W) {
                         o[x] = res[j][x];
+                        sink.store1(y_g, gx + x, W, res[j][x]);
                         n_nan += (res[j][x] != res[j][x]);
                     }
             }

@@ -1,6 +1,10 @@
 // Batched stage A + B: one C call for many views (the host language pays one FFI crossing per batch).
 #include "vs_common.cuh"
 
+bool vs_peer_plan_for(const vs_ctx* ctx, const float* plane, int64_t plane_stride, VsPeerPlan* plan);
+int vs_grid_finalize_peer(vs_ctx* ctx, const uint32_t* keygrid, int xsize, int ysize, float* dsm_out, int simd_lanes,
+                          uint64_t* nan_count, const VsPeerPlan& plan, cudaStream_t stream);
+
 extern "C" {
 
 int vs_views_to_dsm(vs_ctx* ctx, int32_t n_views, const float* const* depth, const int32_t* H, const int32_t* W,
@@ -63,8 +67,17 @@ int vs_views_to_dsm(vs_ctx* ctx, int32_t n_views, const float* const* depth, con
                                     stats ? stats + (size_t)v * VS_NUM_STATS : nullptr, st);
         if (rc) return rc;
         if (ctx->timing) VS_CUDA(cudaEventRecord(ctx->ev_pool[ctx->ev_used + 1], st));
-        rc = vs_grid_finalize(ctx, kg, xs, ys, dsm_stack + (size_t)v * plane_stride, simd_lanes,
-                              nan_counts ? nan_counts + v : nullptr, st);
+        float* plane = dsm_stack + (size_t)v * plane_stride;
+        if (ctx->xch_on) {   // stage B also stores each row into the band stacks of the ranks that fuse it
+            VsPeerPlan plan;
+            if (!vs_peer_plan_for(ctx, plane, plane_stride, &plan)) {
+                vs_set_error("vs_views_to_dsm: dsm_stack plane is not a plane of vs_exchange.local_stack");
+                return VS_ERR_INVALID;
+            }
+            rc = vs_grid_finalize_peer(ctx, kg, xs, ys, plane, simd_lanes, nan_counts ? nan_counts + v : nullptr, plan, st);
+        } else {
+            rc = vs_grid_finalize(ctx, kg, xs, ys, plane, simd_lanes, nan_counts ? nan_counts + v : nullptr, st);
+        }
         if (rc) return rc;
         if (ctx->timing) {
             VS_CUDA(cudaEventRecord(ctx->ev_pool[ctx->ev_used + 2], st));

@@ -41,6 +41,16 @@ struct VsGeoParams {
     int xsize, ysize;
 };
 
+// Kernel-side description of the peer stores of stage B (vs_set_exchange): passed by value to k_grid_finalize.
+// plane[j] = rank j's (rows_j + halo rows) x W plane of the view being finalised, as mapped into this process.
+struct VsPeerPlan {
+    int n;                           // ranks; 0 = no peer stores
+    int halo;
+    unsigned inv;                    // floor(2^32 * n / H): y * inv >> 32 ~ band of row y
+    int row0[VS_MAX_RANKS + 1];      // band boundaries; row0[n] = H
+    float* plane[VS_MAX_RANKS];
+};
+
 struct vs_ctx {
     int device;
     bool aoi_set;
@@ -64,6 +74,9 @@ struct vs_ctx {
     size_t keygrid_extra_cells;
     int n_streams;      // VISSAT_STREAMS=1..4 (default 4: measured 4.66 / 3.78 / 3.49 / 3.45 ms per C2 step for 1..4)
     // optional per-view kernel timing of vs_views_to_dsm
+    // peer-store exchange of stage B (exchange.cu)
+    bool xch_on;
+    vs_exchange xch;
     bool timing;
     std::vector<cudaEvent_t> ev_pool;   // 3 events per logged view: before A, between A and B, after B
     size_t ev_used;

@@ -7,7 +7,16 @@ independent per cell -> each rank owns a contiguous band of grid rows (+1 halo r
 file-system hand-off of aggregate_2p5d.py:57-66.  The result is independent of the number of ranks.
 
 The host logic here runs on any backend (tests use gloo on CPU tensors); the compute calls need CUDA.
+
+Two transports for that transpose:
+  * `PeerExchange` (default on NVLink boxes): stage B's kernel stores every output row straight into the band stack of
+    the rank that fuses it, through CUDA-IPC peer-mapped memory -- compute and exchange are one kernel, there is no
+    pack/copy pass and no collective on the data path (only a 1-element all-reduce as the stream-ordered barrier);
+  * `WaveExchanger`: grouped NCCL send/recv in waves, overlapped with stages A/B of later views (also what the gloo CPU
+    tests exercise).
 """
+import ctypes as C
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -136,6 +145,148 @@ class WaveExchanger:
             torch.cuda.current_stream(self.local.device).wait_stream(self.stream)
         self._reqs = []
         return self.band_stack, self.bands[self.rank], (self.h0, self.h1)
+
+
+class _DeviceArray:
+    """Device memory owned by libvissat_b200 (vs_peer_alloc / vs_peer_open) exposed through
+    __cuda_array_interface__ so that torch can wrap it without a copy."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {'shape': tuple(int(x) for x in shape), 'typestr': '<f4', 'data': (int(ptr), False),
+                                         'version': 3, 'strides': None}
+
+
+class PeerExchange:
+    """Row-band exchange written by stage B itself (vs_set_exchange, include/vissat_b200.h).
+
+    Every rank owns `buffers` band stacks (V_total, rows + halo, W) allocated by the library and mapped into every
+    other rank's address space (CUDA IPC; the handles travel through all_gather_object).  `begin_step()` points the
+    engine at the next stack of every rank; the following `engine.views_to_dsm(..., local_stack, ...)` calls then
+    write both the local per-view DSMs and the remote row bands.  `finish()` is the stream-ordered barrier (1-element
+    all-reduce: every rank's stage-B kernels have completed, hence their peer stores have landed) and returns this
+    rank's stack.  Two stacks alternate so that step s+1 may write while a slower rank still fuses step s.
+    """
+
+    def __init__(self, engine, local_stack, view_counts, group=None, halo=1, buffers=2):
+        from . import _native
+        self._native = _native
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        if self.world > _native.VS_MAX_RANKS:
+            raise ValueError('PeerExchange supports up to {} ranks'.format(_native.VS_MAX_RANKS))
+        self.engine = engine
+        self.local = local_stack
+        self.view_counts = list(view_counts)
+        self.halo = int(halo)
+        self.n_rows, self.W = local_stack.shape[1], local_stack.shape[2]
+        assert (self.n_rows, self.W) == (engine.n_size, engine.e_size)
+        self.bands = row_bands(self.n_rows, self.world)
+        self.bands_h = [band_with_halo(b, self.n_rows, halo) for b in self.bands]
+        self.h0, self.h1 = self.bands_h[self.rank]
+        self.v_total = sum(self.view_counts)
+        self.view0 = sum(self.view_counts[:self.rank])
+        self.n_buffers = int(buffers)
+        lib, check = _native.lib, _native.check
+        ctx = engine.ctx.handle
+        my_rows = self.h1 - self.h0
+        nbytes = max(self.v_total * my_rows * self.W * 4, 4)
+        # Set-up failures must be seen by every rank (a rank that raised alone would leave the others in a collective):
+        # each phase ends with an exchange of success flags.
+        self._own, self._opened, self._ptrs, handles, err = [], [], [], [], None
+        try:
+            for _ in range(self.n_buffers):
+                ptr = C.c_void_p()
+                hbuf = (C.c_uint8 * _native.VS_IPC_HANDLE_BYTES)()
+                check(lib.vs_peer_alloc(ctx, nbytes, C.byref(ptr), hbuf), 'vs_peer_alloc')
+                self._own.append(ptr.value)
+                handles.append(bytes(hbuf))
+        except Exception as e:
+            err, handles = e, None
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, handles, group=group)
+        if any(g is None for g in gathered):
+            self._release()
+            raise _native.VisSatError('PeerExchange: allocation failed on rank(s) {}: {}'.format(
+                [r for r, g in enumerate(gathered) if g is None], err))
+        try:
+            for b in range(self.n_buffers):   # [buffer][rank] -> device pointer valid in this process
+                row = []
+                for r in range(self.world):
+                    if r == self.rank:
+                        row.append(self._own[b])
+                        continue
+                    ptr = C.c_void_p()
+                    hbuf = (C.c_uint8 * _native.VS_IPC_HANDLE_BYTES).from_buffer_copy(gathered[r][b])
+                    check(lib.vs_peer_open(ctx, hbuf, C.byref(ptr)), 'vs_peer_open')
+                    self._opened.append(ptr.value)
+                    row.append(ptr.value)
+                self._ptrs.append(row)
+        except Exception as e:
+            err = e
+        # also the barrier "every rank has mapped every stack before anyone writes"
+        ok = torch.tensor([0 if err is not None else 1], dtype=torch.int32, device=local_stack.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) != 1:
+            self._release()
+            raise _native.VisSatError('PeerExchange: mapping peer memory failed on some rank: {}'.format(err))
+        self.band_stacks = [torch.as_tensor(_DeviceArray(p, (self.v_total, my_rows, self.W)), device=local_stack.device)
+                            for p in self._own]
+        self._flag = torch.zeros(1, dtype=torch.int32, device=local_stack.device)
+        self._cur = -1
+
+    def _release(self):
+        lib, ctx = self._native.lib, self.engine.ctx.handle
+        for p in self._opened:
+            lib.vs_peer_close(ctx, C.c_void_p(p))
+        self._opened = []
+        for p in self._own:
+            lib.vs_peer_free(ctx, C.c_void_p(p))
+        self._own = []
+
+    def begin_step(self):
+        self._cur = (self._cur + 1) % self.n_buffers
+        if self.local.shape[0] == 0:           # a rank without views launches nothing; it still takes part in finish()
+            return
+        ex = self._native.vs_exchange()
+        ex.n_ranks, ex.rank, ex.halo = self.world, self.rank, self.halo
+        ex.view0, ex.n_views_total = self.view0, self.v_total
+        ex.local_stack = self.local.data_ptr()
+        for r in range(self.world):
+            ex.band_stack[r] = self._ptrs[self._cur][r]
+        self.engine.set_exchange(ex)
+
+    def finish(self):
+        """Barrier on the current stream, then this rank's (V_total, rows + halo, W) stack of the step."""
+        self.engine.set_exchange(None)
+        dist.all_reduce(self._flag, group=self.group)
+        return self.band_stacks[self._cur], self.bands[self.rank], (self.h0, self.h1)
+
+    def close(self):
+        lib, ctx = self._native.lib, self.engine.ctx.handle
+        torch.cuda.synchronize(self.local.device)
+        self.engine.set_exchange(None)
+        dist.barrier(group=self.group)         # nobody is still writing into a stack that is about to be unmapped
+        self.band_stacks = []
+        for p in self._opened:
+            lib.vs_peer_close(ctx, C.c_void_p(p))
+        self._opened = []
+        dist.barrier(group=self.group)         # every mapping is gone before the owner frees the memory
+        for p in self._own:
+            lib.vs_peer_free(ctx, C.c_void_p(p))
+        self._own = []
+
+
+def make_exchange(engine, local_stack, view_counts, group=None, prefer='peer'):
+    """PeerExchange when every rank can set it up (its constructor fails on all ranks or on none), else WaveExchanger.
+    Returns (exchanger, kind)."""
+    if prefer == 'peer' and local_stack.is_cuda:
+        try:
+            return PeerExchange(engine, local_stack, view_counts, group=group), 'peer-store'
+        except Exception as e:      # e.g. no peer access between the devices, IPC not permitted in this container
+            if dist.get_rank(group) == 0:
+                print('PeerExchange unavailable ({}); using NCCL waves'.format(e), flush=True)
+    return WaveExchanger(local_stack, view_counts, group=group), 'nccl-waves'
 
 
 class _NullCtx:

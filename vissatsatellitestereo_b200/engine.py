@@ -125,6 +125,10 @@ class DsmEngine:
                                   _ptr(self.keygrid), _ptr(out), stack.stride(0), self.simd_lanes,
                                   _ptr(count_nan), C.c_void_p(0), _stream(self.device)), 'vs_views_to_dsm')
 
+    def set_exchange(self, ex):
+        """Enable (a _native.vs_exchange) or disable (None) the peer stores of stage B (distributed.PeerExchange)."""
+        check(lib.vs_set_exchange(self.ctx.handle, C.byref(ex) if ex is not None else None), 'vs_set_exchange')
+
     def set_streams(self, n):
         check(lib.vs_set_streams(self.ctx.handle, int(n)), 'vs_set_streams')
 
