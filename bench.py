@@ -202,6 +202,11 @@ def run_b200_arm(args, cfg):
     E.require_cuda()
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
+    # run on the CPUs of this GPU's NUMA node: the pinned staging buffers of the e2e leg are then allocated there
+    # (several ranks stream 1.7 GB per step over PCIe at once).  Undone before the CPU baseline is timed.
+    from vissatsatellitestereo_b200 import hostbind
+    affinity0 = os.sched_getaffinity(0) if hasattr(os, 'sched_getaffinity') else None
+    numa_node = hostbind.bind_to_gpu_numa_node(local_rank)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     assert world == args.gpus, 'launch with torchrun --nproc-per-node {} (WORLD_SIZE={})'.format(args.gpus, world)
@@ -387,13 +392,15 @@ def run_b200_arm(args, cfg):
             t_e2e = float(t.item())
         e2e = {'value': mpix_step / t_e2e, 'unit': UNIT, 'h2d_bytes_per_step': int(V * P * 4) * world,
                'd2h_bytes_per_step': int(V * G * 4) * world + (G * 4 if cfg.fuse else 0), 'ms_per_step': 1e3 * t_e2e,
-               'steps': n_e2e, 'api': 'DsmEngine.process_host (pinned host buffers in/out, 3 streams)' +
+               'steps': n_e2e, 'host_numa_node': numa_node, 'api': 'DsmEngine.process_host (pinned host buffers in/out, 3 streams)' +
                ('' if world == 1 else ' per rank + NCCL row-band exchange + per-rank fused band to host')}
         if cfg.fuse and world == 1:
             assert np.array_equal(host_fused.numpy(), fused.cpu().numpy(), equal_nan=True), 'e2e result differs'
 
     if peer:
         xch.close()
+    if affinity0 is not None:
+        os.sched_setaffinity(0, affinity0)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

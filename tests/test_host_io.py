@@ -117,3 +117,31 @@ def test_rowband_exchange_world2_gloo(n_rows, counts):
     out = mgr.dict()
     mp.spawn(_exchange_worker, args=(world, port, n_rows, 11, counts, out), nprocs=world, join=True)
     assert dict(out) == {0: True, 1: True}
+
+
+def test_bind_to_gpu_numa_node_with_fake_sysfs(tmp_path, monkeypatch):
+    """hostbind: affinity follows <sysfs>/bus/pci/devices/<bus>/numa_node -> node<N>/cpulist; unknown -> unchanged."""
+    import os
+    from vissatsatellitestereo_b200 import hostbind as HB
+    assert HB._parse_cpulist('0-3,8,10-11\n') == {0, 1, 2, 3, 8, 10, 11}
+    if not hasattr(os, 'sched_setaffinity'):
+        return
+    allowed = sorted(os.sched_getaffinity(0))
+    monkeypatch.setattr(HB, 'gpu_pci_bus_id', lambda i: '0000:1b:00.0')
+    sysfs = tmp_path / 'sys'
+    (sysfs / 'bus/pci/devices/0000:1b:00.0').mkdir(parents=True)
+    (sysfs / 'devices/system/node/node1').mkdir(parents=True)
+    assert HB.bind_to_gpu_numa_node(0, str(sysfs)) == -1                 # no numa_node file
+    (sysfs / 'bus/pci/devices/0000:1b:00.0/numa_node').write_text('-1\n')
+    assert HB.bind_to_gpu_numa_node(0, str(sysfs)) == -1                 # kernel does not know
+    (sysfs / 'bus/pci/devices/0000:1b:00.0/numa_node').write_text('1\n')
+    (sysfs / 'devices/system/node/node1/cpulist').write_text('{}\n'.format(allowed[0]))
+    try:
+        assert HB.gpu_numa_node(0, str(sysfs)) == 1
+        assert HB.bind_to_gpu_numa_node(0, str(sysfs)) == 1
+        assert os.sched_getaffinity(0) == {allowed[0]}
+        (sysfs / 'devices/system/node/node1/cpulist').write_text('100000\n')   # none of our CPUs: leave as is
+        assert HB.bind_to_gpu_numa_node(0, str(sysfs)) == -1
+        assert os.sched_getaffinity(0) == {allowed[0]}
+    finally:
+        os.sched_setaffinity(0, set(allowed))

@@ -39,6 +39,50 @@ __host__ __device__ __forceinline__ T vs_poly_eval(const T* __restrict__ c, T u,
     return r;
 }
 
+#ifdef __CUDACC__
+// float32, L points (L even) in lockstep on sm_100's packed FFMA2: one instruction does the Horner step of two points
+// (the coefficient is a broadcast scalar operand), which halves the issue slots of the float32 part.  Each lane is an
+// IEEE fma, so the result is bit-identical to vs_poly_eval<D, float>.
+template <int D, int L>
+__device__ __forceinline__ void vs_poly_eval_n_f32x2(const float* __restrict__ c, const float (&u)[L], const float (&v)[L],
+                                                     const float (&w)[L], float (&out)[L]) {
+    static_assert(L % 2 == 0, "pairs of points");
+    constexpr int H = L / 2;
+    float2 U[H], V[H], W[H], r[H], a[H], b[H];
+#pragma unroll
+    for (int p = 0; p < H; ++p) {
+        U[p] = make_float2(u[2 * p], u[2 * p + 1]);
+        V[p] = make_float2(v[2 * p], v[2 * p + 1]);
+        W[p] = make_float2(w[2 * p], w[2 * p + 1]);
+    }
+#pragma unroll
+    for (int i = D; i >= 0; --i) {
+#pragma unroll
+        for (int j = D - i; j >= 0; --j) {
+            const int kmax = D - i - j;
+            const float ck = c[vs_poly_index(D, i, j, kmax)];
+#pragma unroll
+            for (int p = 0; p < H; ++p) b[p] = make_float2(ck, ck);
+#pragma unroll
+            for (int k = kmax - 1; k >= 0; --k) {
+                const float cc = c[vs_poly_index(D, i, j, k)];
+#pragma unroll
+                for (int p = 0; p < H; ++p) b[p] = __ffma2_rn(b[p], W[p], make_float2(cc, cc));
+            }
+#pragma unroll
+            for (int p = 0; p < H; ++p) a[p] = (j == D - i) ? b[p] : __ffma2_rn(a[p], V[p], b[p]);
+        }
+#pragma unroll
+        for (int p = 0; p < H; ++p) r[p] = (i == D) ? a[p] : __ffma2_rn(r[p], U[p], a[p]);
+    }
+#pragma unroll
+    for (int p = 0; p < H; ++p) {
+        out[2 * p] = r[p].x;
+        out[2 * p + 1] = r[p].y;
+    }
+}
+#endif
+
 // The same evaluation for L points in lockstep (terms outer, points inner): every coefficient is fetched once
 // and used L times, which matters on sm_100a where a DFMA cannot take a constant-bank operand.
 // Bit-identical to L calls of vs_poly_eval.

@@ -242,7 +242,7 @@ k_unproject_scatter(RasterParams p, PolyCoefs pc, const VsExactParams* __restric
             if (D64 > 0) {
                 vs_poly_eval_n<(D64 > 0 ? D64 : 1), PX, double>(pc.c64[o], u, v, w, val);
                 float hi[PX];
-                vs_poly_eval_n<D, PX, float>(pc.c32[o], uf, vf, wf, hi);
+                vs_poly_eval_n_f32x2<D, PX>(pc.c32[o], uf, vf, wf, hi);
 #pragma unroll
                 for (int i = 0; i < PX; ++i) val[i] += (double)hi[i];
             } else {
