@@ -40,6 +40,12 @@ __device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
     return r;
 }
 
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+__device__ __forceinline__ void cp_async_wait_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+
 // block-level reduction of the per-thread counters, one atomic per counter per block
 __device__ __forceinline__ void flush_stats(unsigned long long* stats, unsigned v0, unsigned v1, unsigned v2, unsigned v3) {
     if (stats == nullptr) return;
@@ -168,8 +174,28 @@ k_unproject_scatter(RasterParams p, PolyCoefs pc, const VsExactParams* __restric
     const bool want_hm = height_map != nullptr;
     unsigned cnt[4] = {0, 0, 0, 0};
 
-    for (unsigned chunk = blockIdx.x * blockDim.x + threadIdx.x; chunk < n_chunks; chunk += gridDim.x * blockDim.x) {
+    // Row pitch a multiple of PX (the usual case): no chunk straddles a row and chunk c is the aligned float4 c, so the
+    // depth of the NEXT chunk of this thread is requested (cp.async into a per-thread shared-memory slot, no registers
+    // held) before the current one is processed; the global-load latency is otherwise exposed once per iteration and
+    // the kernel has only 24 warps per SM to hide it with.  Each thread reads only its own slot: no block barrier.
+    __shared__ __align__(16) float4 s_pre[2][kThreads];
+    const bool simple = (p.W % PX) == 0;
+    const unsigned n_full = (unsigned)(n_pix / PX);
+    const unsigned stride = gridDim.x * blockDim.x;
+    const float4* __restrict__ depth4 = reinterpret_cast<const float4*>(depth);
+    int stage = 0;
+    {
+        const unsigned first = blockIdx.x * blockDim.x + threadIdx.x;
+        if (simple && first < n_full) cp_async16(&s_pre[0][threadIdx.x], depth4 + first);
+        cp_async_commit();
+    }
+    for (unsigned chunk = blockIdx.x * blockDim.x + threadIdx.x; chunk < n_chunks; chunk += stride) {
         const unsigned base = chunk * PX;
+        if (simple && chunk + stride < n_full) cp_async16(&s_pre[stage ^ 1][threadIdx.x], depth4 + (chunk + stride));
+        cp_async_commit();
+        cp_async_wait_but_one();
+        const float4 cur = s_pre[stage][threadIdx.x];
+        stage ^= 1;
         // row = base / W by multiply-shift (magic = ceil(2^48 / W), exact for base < 2^32, W < 2^16)
         const unsigned row0 = (unsigned)(((unsigned long long)base * p.w_magic) >> 48);
         const unsigned col0 = base - row0 * (unsigned)p.W;
@@ -177,7 +203,7 @@ k_unproject_scatter(RasterParams p, PolyCoefs pc, const VsExactParams* __restric
             scatter_chunk_generic<D, D64>(p, pc, ex, depth, base, n_pix, keygrid, height_map, audit, cnt);
             continue;
         }
-        const float4 t4 = ld_stream_f4(reinterpret_cast<const float4*>(depth + base));
+        const float4 t4 = simple ? cur : ld_stream_f4(reinterpret_cast<const float4*>(depth + base));
         const float d4[PX] = {t4.x, t4.y, t4.z, t4.w};
         // aggregate_2p5d_util.py:76: depth <= 0 (and NaN) is invalid
         if (!(d4[0] > 0.0f || d4[1] > 0.0f || d4[2] > 0.0f || d4[3] > 0.0f)) {
@@ -427,7 +453,15 @@ int vs_unproject_rasterize(vs_ctx* ctx, const float* depth, int32_t H, int32_t W
             memcpy(pc.c64, P.coef, sizeof(pc.c64));
         }
         const VsExactParams* ex = reinterpret_cast<const VsExactParams*>(ctx->d_exact);
-        const int grid = persistent_grid(ctx, (n_pix + PX - 1) / PX, 8);
+        // One wave of resident CTAs (3 per SM for the d64 == 1 variant, 2 otherwise; __launch_bounds__ above): longer
+        // grid-stride loops keep the prefetch pipeline full and avoid a partial last wave (measured on C2: 3.24 ms per
+        // step with 3 CTAs per SM, 3.27 / 3.30 / 3.34 with 6 / 8 / 12).  VISSAT_K1_CTAS_PER_SM overrides.
+        static const int k1_ctas_env = []() {
+            const char* e = getenv("VISSAT_K1_CTAS_PER_SM");
+            const int v = e ? atoi(e) : 0;
+            return v < 0 ? 0 : (v > 32 ? 32 : v);
+        }();
+        const int grid = persistent_grid(ctx, (n_pix + PX - 1) / PX, k1_ctas_env ? k1_ctas_env : (P.d64 == 1 ? 3 : 2));
 #define VS_LAUNCH_K1(DEG, LO) \
     k_unproject_scatter<DEG, LO><<<grid, kThreads, 0, stream>>>(p, pc, ex, depth, keygrid, height_map, d_stats)
         switch (P.degree * 3 + P.d64) {
