@@ -136,7 +136,8 @@ def _tiny_engine(eng_mod, lanes):
 
 
 # ------------------------------------------------------------------------------------------------ fusion alone
-@pytest.mark.parametrize('V', [1, 2, 3, 4, 7, 8, 9, 16, 23, 33, 50, 56, 57, 64, 65, 100, 128, 129, 136, 200, 257, 300, 400, 512, 513, 700, 1025, 2048])
+@pytest.mark.parametrize('V', [1, 2, 3, 4, 7, 8, 9, 16, 23, 33, 36, 37, 43, 44, 50, 52, 56, 57, 60, 61, 64, 65, 81, 88, 100, 104, 113, 120, 128, 129, 136, 200,
+                               208, 257, 300, 400, 416, 512, 513, 700, 1025, 2048])
 def test_fusion_bit_exact_vs_numpy(eng_mod, lanes, V):
     eng = _tiny_engine(eng_mod, lanes)
     rng = np.random.default_rng(V)

@@ -77,7 +77,8 @@ def main():
         print('k4 median3x3 {:.1f} us  {:.0f} GB/s (8 B/cell)'.format(t * 1e3, 8 * G / t / 1e6))
     if 'fuse' in what:
         base = torch.stack([eng.view_dsm(depths[v], mats[v]).clone() for v in range(4)])
-        for V, rows in ((8, 2048), (50, 2048), (64, 2048), (100, 1024), (200, 512), (400, 256)):
+        for V, rows in ((8, 2048), (16, 2048), (24, 2048), (32, 2048), (40, 2048), (50, 2048), (64, 2048), (100, 1024),
+                        (200, 512), (400, 256)):
             idx = torch.arange(V, device=dev) % 4
             stack = (base[idx, :rows] + torch.randn((V, 1, 1), device=dev) * 0.5).contiguous()
             stack[torch.rand(stack.shape, device=dev) < 0.1] = float('nan')

@@ -11,8 +11,10 @@
 // so every per-view load is a coalesced 128-byte line per warp; each plane element is read from HBM once
 // (the re-reads of passes 2 and 3 hit L1/L2).  Algorithmic traffic: 4V bytes read + 4 bytes written per cell.
 //
-// V <= 64: values live in registers and are sorted with a Batcher merge-exchange network (sortnets_gen.cuh),
-//          branch-free.  V > 64: 8 or 32 threads per cell, sorted runs in shared memory (k_fuse_large).
+// V <= 32:  k_fuse_small  -- original and sorted values both in registers, Batcher merge-exchange network
+//            (sortnets_gen.cuh), branch-free.
+// V <= 128: k_fuse_medium -- only the sorted copy in registers, originals re-read from L2 for the sum.
+// V > 128:  k_fuse_large  -- 4, 8 or 32 threads per cell, sorted runs in shared memory, bitwise bisection.
 #include <math_constants.h>
 
 #include "sortnets_gen.cuh"
@@ -34,13 +36,20 @@ VS_DEF_SORTNET(8)
 VS_DEF_SORTNET(16)
 VS_DEF_SORTNET(24)
 VS_DEF_SORTNET(32)
+VS_DEF_SORTNET(36)
 VS_DEF_SORTNET(40)
+VS_DEF_SORTNET(44)
 VS_DEF_SORTNET(48)
+VS_DEF_SORTNET(52)
 VS_DEF_SORTNET(56)
+VS_DEF_SORTNET(60)
 VS_DEF_SORTNET(64)
 VS_DEF_SORTNET(80)
+VS_DEF_SORTNET(88)
 VS_DEF_SORTNET(96)
+VS_DEF_SORTNET(104)
 VS_DEF_SORTNET(112)
+VS_DEF_SORTNET(120)
 VS_DEF_SORTNET(128)
 #undef VS_DEF_SORTNET
 
@@ -94,7 +103,7 @@ __device__ __forceinline__ float pairwise_leaf_static(const F& y, int n) {
     for (int j = 0; j < 8; ++j) r[j] = y(j);
     const int nfull = n - (n & 7);
 #pragma unroll
-    for (int i = 8; i < N; i += 8) {
+    for (int i = 8; i + 8 <= N; i += 8) {   // N need not be a multiple of 8: a full block of 8 never starts past N - 8
         if (i < nfull) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(r[j], y(i + j));
@@ -151,7 +160,7 @@ k_fuse_small(const float* __restrict__ views, int64_t plane_stride, int V, int64
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// medium V (65..128): still one thread per cell and a register sorting network, but only the SORTED copy lives
+// medium V (33..128): still one thread per cell and a register sorting network, but only the SORTED copy lives
 // in registers; the original-order values needed by the pairwise sum are re-read from L2 (KeepFn).
 // ---------------------------------------------------------------------------------------------------------
 struct KeepFn {
@@ -171,7 +180,7 @@ struct KeepFn {
 };
 
 template <int NV>
-__global__ void __launch_bounds__(kBlockSmall)
+__global__ void __launch_bounds__(kBlockSmall, (NV > 64 && NV <= 112) ? 4 : 1)
 k_fuse_medium(const float* __restrict__ views, int64_t plane_stride, int V, int64_t n_cells, float* __restrict__ out) {
     const int64_t cell = blockIdx.x * (int64_t)kBlockSmall + threadIdx.x;
     if (cell >= n_cells) return;
@@ -484,8 +493,8 @@ int launch_large(vs_ctx* ctx, const float* views, int64_t plane_stride, int V, i
     if (V <= LANES * NVL) return launch_large_t<LANES, NVL>(ctx, views, plane_stride, V, n_cells, out, stream);
     // runs of 40..64 values per lane: longer register-sorted runs (80..128) were measured 2x slower (255 registers
     // and > 100 KB of shared memory per CTA leave one CTA per SM)
-    VS_TRY(4, 40) VS_TRY(4, 48) VS_TRY(4, 56) VS_TRY(4, 64)
-    VS_TRY(8, 40) VS_TRY(8, 48) VS_TRY(8, 56) VS_TRY(8, 64)
+    VS_TRY(4, 40) VS_TRY(4, 48) VS_TRY(4, 52) VS_TRY(4, 56) VS_TRY(4, 64)
+    VS_TRY(8, 40) VS_TRY(8, 48) VS_TRY(8, 52) VS_TRY(8, 56) VS_TRY(8, 64)
     VS_TRY(32, 24) VS_TRY(32, 32) VS_TRY(32, 48) VS_TRY(32, 64)
 #undef VS_TRY
     vs_set_error("vs_fuse_views: more than 2048 views");
@@ -512,13 +521,26 @@ extern "C" int vs_fuse_views(vs_ctx* ctx, const float* views, int64_t plane_stri
     if (V <= 16) return launch_small<16>(ctx, views, plane_stride, V, n_cells, out_mean, stream);
     if (V <= 24) return launch_small<24>(ctx, views, plane_stride, V, n_cells, out_mean, stream);
     if (V <= 32) return launch_small<32>(ctx, views, plane_stride, V, n_cells, out_mean, stream);
-    if (V <= 40) return launch_small<40>(ctx, views, plane_stride, V, n_cells, out_mean, stream);
-    if (V <= 48) return launch_small<48>(ctx, views, plane_stride, V, n_cells, out_mean, stream);
-    if (V <= 56) return launch_small<56>(ctx, views, plane_stride, V, n_cells, out_mean, stream);
-    if (V <= 64) return launch_small<64>(ctx, views, plane_stride, V, n_cells, out_mean, stream);
+    // network sizes in steps of 4 above 32 views (the network for 52 wires has 9 % fewer comparators than the one
+    // for 56), steps of 8 above 64
+    // Above 32 views the one-array kernel (sorted copy in registers, originals re-read from L2) wins: 75..80 registers
+    // and 24 warps per SM against 113..188 registers for the two-array kernel (measured, 2048^2 cells: V = 40
+    // 356 vs 383 us, V = 50 482 vs 585 us, V = 64 653 vs 966 us).  Network sizes in steps of 4 up to 64 views (the
+    // network for 52 wires has 9 % fewer comparators than the one for 56), steps of 8 above.
+    if (V <= 36) return launch_medium<36>(ctx, views, plane_stride, V, n_cells, out_mean, stream);
+    if (V <= 40) return launch_medium<40>(ctx, views, plane_stride, V, n_cells, out_mean, stream);
+    if (V <= 44) return launch_medium<44>(ctx, views, plane_stride, V, n_cells, out_mean, stream);
+    if (V <= 48) return launch_medium<48>(ctx, views, plane_stride, V, n_cells, out_mean, stream);
+    if (V <= 52) return launch_medium<52>(ctx, views, plane_stride, V, n_cells, out_mean, stream);
+    if (V <= 56) return launch_medium<56>(ctx, views, plane_stride, V, n_cells, out_mean, stream);
+    if (V <= 60) return launch_medium<60>(ctx, views, plane_stride, V, n_cells, out_mean, stream);
+    if (V <= 64) return launch_medium<64>(ctx, views, plane_stride, V, n_cells, out_mean, stream);
     if (V <= 80) return launch_medium<80>(ctx, views, plane_stride, V, n_cells, out_mean, stream);
+    if (V <= 88) return launch_medium<88>(ctx, views, plane_stride, V, n_cells, out_mean, stream);
     if (V <= 96) return launch_medium<96>(ctx, views, plane_stride, V, n_cells, out_mean, stream);
+    if (V <= 104) return launch_medium<104>(ctx, views, plane_stride, V, n_cells, out_mean, stream);
     if (V <= 112) return launch_medium<112>(ctx, views, plane_stride, V, n_cells, out_mean, stream);
+    if (V <= 120) return launch_medium<120>(ctx, views, plane_stride, V, n_cells, out_mean, stream);
     if (V <= 128) return launch_medium<128>(ctx, views, plane_stride, V, n_cells, out_mean, stream);
     return launch_large(ctx, views, plane_stride, V, n_cells, out_mean, stream);
 }
