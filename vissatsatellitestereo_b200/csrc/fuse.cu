@@ -27,7 +27,8 @@ constexpr int kBlockSmall = 128;
 template <int N> struct SortNet;
 #define VS_DEF_SORTNET(N)                                                     \
     template <> struct SortNet<N> {                                           \
-        static __device__ __forceinline__ void sort(float (&a)[N]) {          \
+        template <int M>                                                      \
+        static __device__ __forceinline__ void sort(float (&a)[M]) {          \
             VS_SORTNET_##N(VS_CE_REG)                                         \
         }                                                                     \
     };
@@ -273,20 +274,46 @@ __device__ __forceinline__ int run_lower_bound(const uint32_t* __restrict__ run,
     return lb;
 }
 
+// The same lower bound with the first three levels of the search done on 7 splitter keys held in registers
+// (sp[j] = run element (j+1)*P/8 - 1): three dependent shared-memory probes fewer per call.  The bisection below calls
+// it 31..32 times per order statistic and is bound by exactly that dependent-load latency.
+template <int LANES, int NVL>
+__device__ __forceinline__ void run_load_splitters(const uint32_t* __restrict__ run, uint32_t (&sp)[7]) {
+    constexpr int B = RunPad<NVL>::value / 8;
+#pragma unroll
+    for (int j = 0; j < 7; ++j) sp[j] = run[((j + 1) * B - 1) * LANES];
+}
+template <int LANES, int NVL>
+__device__ __forceinline__ int run_lower_bound_sp(const uint32_t* __restrict__ run, const uint32_t (&sp)[7], uint32_t T) {
+    constexpr int B = RunPad<NVL>::value / 8;
+    const bool c1 = sp[3] < T;
+    const uint32_t s2 = c1 ? sp[5] : sp[1];
+    const bool c2 = s2 < T;
+    const uint32_t s3 = c1 ? (c2 ? sp[6] : sp[4]) : (c2 ? sp[2] : sp[0]);
+    const bool c3 = s3 < T;
+    int lb = (c1 ? 4 * B : 0) + (c2 ? 2 * B : 0) + (c3 ? B : 0);
+#pragma unroll
+    for (int step = B / 2; step >= 1; step >>= 1)
+        if (run[(lb + step - 1) * LANES] < T) lb += step;
+    return lb;
+}
+
 // keys of rank r_hi and r_hi-1 (0-based) in the union of the group's runs; k_lo_out = k_hi if want_lo is false
 template <int LANES, int NVL>
 __device__ __forceinline__ void group_select(const uint32_t* __restrict__ run, int r_hi, bool want_lo, unsigned mask,
                                              uint32_t start_key, int start_bit, uint32_t& k_hi_out, uint32_t& k_lo_out) {
+    uint32_t sp[7];
+    run_load_splitters<LANES, NVL>(run, sp);
     uint32_t K = start_key;
     for (int b = start_bit; b >= 0; --b) {  // largest K with count(keys < K) <= r_hi  ==  the r_hi-th smallest key
         const uint32_t T = K | (1u << b);
-        const int c = group_sum<LANES>(run_lower_bound<LANES, NVL>(run, T), mask);
+        const int c = group_sum<LANES>(run_lower_bound_sp<LANES, NVL>(run, sp, T), mask);
         if (c <= r_hi) K = T;
     }
     k_hi_out = K;
     k_lo_out = K;
     if (want_lo) {
-        const int lb = run_lower_bound<LANES, NVL>(run, K);
+        const int lb = run_lower_bound_sp<LANES, NVL>(run, sp, K);
         const int below = group_sum<LANES>(lb, mask);
         if (below == r_hi) {  // rank r_hi-1 is the largest key below K
             const uint32_t mine = lb > 0 ? run[(lb - 1) * LANES] : 0u;
@@ -295,77 +322,11 @@ __device__ __forceinline__ void group_select(const uint32_t* __restrict__ run, i
     }
 }
 
-template <int LANES, int NVL>
-__global__ void __launch_bounds__(kLargeThreads)
-k_fuse_large(const float* __restrict__ views, int64_t plane_stride, int V, int64_t n_cells, int VS,
-             float* __restrict__ out) {
-    constexpr int CELLS = kLargeThreads / LANES;  // cells per CTA
-    extern __shared__ uint32_t s_tile[];          // CELLS x VS words: floats first, then keys
-    const int tid = threadIdx.x;
-    const int64_t cell0 = blockIdx.x * (int64_t)CELLS;
-
-    // 1. coalesced load: consecutive threads read consecutive cells of one view plane
-    for (int i = tid; i < CELLS * V; i += kLargeThreads) {
-        const int v = i / CELLS, c = i - v * CELLS;
-        const int64_t cell = cell0 + c;
-        float t = CUDART_NAN_F;
-        if (cell < n_cells) t = __ldg(views + (int64_t)v * plane_stride + cell);
-        s_tile[c * VS + v] = __float_as_uint(t);
-    }
-    __syncthreads();
-
-    const int c_local = tid / LANES, lane = tid % LANES;
-    const int64_t cell = cell0 + c_local;
-    const unsigned gmask = LANES == 32 ? 0xffffffffu : (((1u << LANES) - 1u) << ((tid & 31) / LANES * LANES));
-    uint32_t* run = s_tile + c_local * VS + lane;  // element i of this lane's run: run[i * LANES]
-
-    // 2. per-lane sorted run
-    float s[NVL];
-    int k_lane = 0;
-#pragma unroll
-    for (int i = 0; i < NVL; ++i) {
-        const int v = lane + i * LANES;
-        float t = CUDART_INF_F;
-        if (v < V) {
-            const float x = __uint_as_float(run[i * LANES]);
-            if (x == x) {
-                t = x;
-                ++k_lane;
-            }
-        }
-        s[i] = t;
-    }
-    const int k = group_sum<LANES>(k_lane, gmask);
-    if (cell >= n_cells) return;       // whole group leaves together
-    if (k <= 2) {                      // aggregate_2p5d.py:69-71
-        if (lane == 0) out[cell] = CUDART_NAN_F;
-        return;
-    }
-    SortNet<NVL>::sort(s);
-#pragma unroll
-    for (int i = 0; i < NVL; ++i) run[i * LANES] = vs_key32(s[i]);
-#pragma unroll
-    for (int i = NVL; i < RunPad<NVL>::value; ++i) run[i * LANES] = 0xffffffffu;   // pads: never below any threshold
-    __syncwarp(gmask);
-
-    // 3. median
-    const int ilo = (k - 1) >> 1, ihi = k >> 1;
-    uint32_t khi, klo;
-    group_select<LANES, NVL>(run, ihi, ilo != ihi, gmask, 0u, 31, khi, klo);
-    const float med = __fdiv_rn(__fadd_rn(vs_unkey32(klo), vs_unkey32(khi)), 2.0f);
-    __syncwarp(gmask);
-
-    // 4. MAD: |sorted run - med| is bitonic per lane -> merge in registers -> runs of keys again
-#pragma unroll
-    for (int i = 0; i < NVL; ++i) s[i] = fabsf(__fsub_rn(s[i], med));
-    bitonic_merge_regs<NVL>(s);
-#pragma unroll
-    for (int i = 0; i < NVL; ++i) run[i * LANES] = vs_key32(s[i]);
-    __syncwarp(gmask);
-    group_select<LANES, NVL>(run, ihi, ilo != ihi, gmask, 0x80000000u, 30, khi, klo);   // deviations are >= 0
-    const float mad = __fdiv_rn(__fadd_rn(vs_unkey32(klo), vs_unkey32(khi)), 2.0f);
-
-    // 5. nanmean of the survivors in numpy's pairwise order: lane j < 8 owns accumulator r[j]
+// nanmean of the survivors of one cell in numpy's pairwise order, computed by the LANES threads of the cell's group
+// (lane j < 8 owns numpy's accumulator r[j]); the views are re-read from L2.  Every lane returns the mean.
+template <int LANES>
+__device__ __forceinline__ float sum_survivors(const float* __restrict__ views, int64_t cell, int64_t plane_stride, int V,
+                                               float med, float mad, int lane, unsigned gmask) {
     const KeepFn y{views + cell, plane_stride, med, mad};
     // numpy's 8 strided accumulators r[0..7] are spread over the first AL = min(LANES, 8) lanes of the group:
     // lane q < AL owns r[q], r[q + AL], ...
@@ -452,7 +413,82 @@ k_fuse_large(const float* __restrict__ views, int64_t plane_stride, int V, int64
         total = stack_val[0];
     }
     cnt = group_sum<LANES>(cnt, gmask);
-    if (lane == 0) out[cell] = __fdiv_rn(total, (float)cnt);
+    return __fdiv_rn(total, (float)cnt);
+}
+
+template <int LANES, int NVL>
+__global__ void __launch_bounds__(kLargeThreads)
+k_fuse_large(const float* __restrict__ views, int64_t plane_stride, int V, int64_t n_cells, int VS,
+             float* __restrict__ out) {
+    constexpr int CELLS = kLargeThreads / LANES;  // cells per CTA
+    extern __shared__ uint32_t s_tile[];          // CELLS x VS words: floats first, then keys
+    const int tid = threadIdx.x;
+    const int64_t cell0 = blockIdx.x * (int64_t)CELLS;
+
+    // 1. coalesced load: consecutive threads read consecutive cells of one view plane
+    for (int i = tid; i < CELLS * V; i += kLargeThreads) {
+        const int v = i / CELLS, c = i - v * CELLS;
+        const int64_t cell = cell0 + c;
+        float t = CUDART_NAN_F;
+        if (cell < n_cells) t = __ldg(views + (int64_t)v * plane_stride + cell);
+        s_tile[c * VS + v] = __float_as_uint(t);
+    }
+    __syncthreads();
+
+    const int c_local = tid / LANES, lane = tid % LANES;
+    const int64_t cell = cell0 + c_local;
+    const unsigned gmask = LANES == 32 ? 0xffffffffu : (((1u << LANES) - 1u) << ((tid & 31) / LANES * LANES));
+    uint32_t* run = s_tile + c_local * VS + lane;  // element i of this lane's run: run[i * LANES]
+
+    // 2. per-lane sorted run
+    float s[NVL];
+    int k_lane = 0;
+#pragma unroll
+    for (int i = 0; i < NVL; ++i) {
+        const int v = lane + i * LANES;
+        float t = CUDART_INF_F;
+        if (v < V) {
+            const float x = __uint_as_float(run[i * LANES]);
+            if (x == x) {
+                t = x;
+                ++k_lane;
+            }
+        }
+        s[i] = t;
+    }
+    const int k = group_sum<LANES>(k_lane, gmask);
+    if (cell >= n_cells) return;       // whole group leaves together
+    if (k <= 2) {                      // aggregate_2p5d.py:69-71
+        if (lane == 0) out[cell] = CUDART_NAN_F;
+        return;
+    }
+    SortNet<NVL>::sort(s);
+#pragma unroll
+    for (int i = 0; i < NVL; ++i) run[i * LANES] = vs_key32(s[i]);
+#pragma unroll
+    for (int i = NVL; i < RunPad<NVL>::value; ++i) run[i * LANES] = 0xffffffffu;   // pads: never below any threshold
+    __syncwarp(gmask);
+
+    // 3. median
+    const int ilo = (k - 1) >> 1, ihi = k >> 1;
+    uint32_t khi, klo;
+    group_select<LANES, NVL>(run, ihi, ilo != ihi, gmask, 0u, 31, khi, klo);
+    const float med = __fdiv_rn(__fadd_rn(vs_unkey32(klo), vs_unkey32(khi)), 2.0f);
+    __syncwarp(gmask);
+
+    // 4. MAD: |sorted run - med| is bitonic per lane -> merge in registers -> runs of keys again
+#pragma unroll
+    for (int i = 0; i < NVL; ++i) s[i] = fabsf(__fsub_rn(s[i], med));
+    bitonic_merge_regs<NVL>(s);
+#pragma unroll
+    for (int i = 0; i < NVL; ++i) run[i * LANES] = vs_key32(s[i]);
+    __syncwarp(gmask);
+    group_select<LANES, NVL>(run, ihi, ilo != ihi, gmask, 0x80000000u, 30, khi, klo);   // deviations are >= 0
+    const float mad = __fdiv_rn(__fadd_rn(vs_unkey32(klo), vs_unkey32(khi)), 2.0f);
+
+    // 5. nanmean of the survivors in numpy's pairwise order
+    const float mean = sum_survivors<LANES>(views, cell, plane_stride, V, med, mad, lane, gmask);
+    if (lane == 0) out[cell] = mean;
 }
 
 template <int NV>
@@ -489,10 +525,11 @@ int launch_large_t(vs_ctx* ctx, const float* views, int64_t plane_stride, int V,
 
 int launch_large(vs_ctx* ctx, const float* views, int64_t plane_stride, int V, int64_t n_cells, float* out,
                  cudaStream_t stream) {
+    // A register-only variant (cross-lane bitonic merge tree with shuffles instead of the bisection) was measured
+    // slower (1.43 vs 1.28 ms for 200 views x 1M cells): three times the min/max instructions, and FMNMX issues on the
+    // half-rate ALU pipe.
 #define VS_TRY(LANES, NVL) \
     if (V <= LANES * NVL) return launch_large_t<LANES, NVL>(ctx, views, plane_stride, V, n_cells, out, stream);
-    // runs of 40..64 values per lane: longer register-sorted runs (80..128) were measured 2x slower (255 registers
-    // and > 100 KB of shared memory per CTA leave one CTA per SM)
     VS_TRY(4, 40) VS_TRY(4, 48) VS_TRY(4, 52) VS_TRY(4, 56) VS_TRY(4, 64)
     VS_TRY(8, 40) VS_TRY(8, 48) VS_TRY(8, 52) VS_TRY(8, 56) VS_TRY(8, 64)
     VS_TRY(32, 24) VS_TRY(32, 32) VS_TRY(32, 48) VS_TRY(32, 64)

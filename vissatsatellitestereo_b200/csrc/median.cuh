@@ -41,6 +41,11 @@ __device__ __forceinline__ float vs_max_t(float a, float b) { return fmaxf(a, b)
 __device__ __forceinline__ double vs_min_t(double a, double b) { return fmin(a, b); }
 __device__ __forceinline__ double vs_max_t(double a, double b) { return fmax(a, b); }
 
+// (lo + hi) / 2 as numpy computes it for a float64 list, rounded to T.  For float the double detour is not needed:
+// halving is an exponent shift, so RN_f32((lo + hi) / 2) == RN_f32(lo + hi) / 2 (no overflow or subnormals for heights).
+__device__ __forceinline__ float vs_mean2(float lo, float hi) { return __fmul_rn(__fadd_rn(lo, hi), 0.5f); }
+__device__ __forceinline__ double vs_mean2(double lo, double hi) { return (lo + hi) * 0.5; }
+
 // Median of the k non-NaN values among 8 candidates (lib/proj_to_grid.py:70-79 -> np.median of a list):
 // odd k -> middle element, even k -> mean of the two middle elements (computed in double, as numpy does
 // for a float64 list), k == 0 -> NaN.  T is float (32-bit key path) or double (64-bit key path).
@@ -63,15 +68,15 @@ __device__ __forceinline__ T vs_median_of_valid8(T (&v)[8]) {
     VS_CE(2, 4) VS_CE(3, 5)
     VS_CE(1, 2) VS_CE(3, 4) VS_CE(5, 6)
 #undef VS_CE
-    // middle elements of the k valid ones: positions (k-1)/2 and k/2, i.e. <= 4, so v[5..7] are never read
+    // middle elements of the k valid ones: positions (k-1)/2 (0..3) and k/2 (0..4), so v[5..7] are never read.
+    // Two-level select on the index bits instead of a compare per candidate.
     const int ilo = (k - 1) >> 1, ihi = k >> 1;
-    T lo = v[0], hi = v[0];
-#pragma unroll
-    for (int i = 1; i <= 4; ++i) {
-        lo = (i == ilo) ? v[i] : lo;
-        hi = (i == ihi) ? v[i] : hi;
-    }
-    const T avg = (T)(((double)lo + (double)hi) * 0.5);   // exact halving; == (lo + hi) / 2.0 in float64
+    const bool lo_b0 = (ilo & 1) != 0, lo_b1 = (ilo & 2) != 0;
+    const bool hi_b0 = (ihi & 1) != 0, hi_b1 = (ihi & 2) != 0;
+    const T lo = lo_b1 ? (lo_b0 ? v[3] : v[2]) : (lo_b0 ? v[1] : v[0]);      // k == 0: ilo = -1 -> v[3]; unused
+    const T hi4 = hi_b1 ? (hi_b0 ? v[3] : v[2]) : (hi_b0 ? v[1] : v[0]);
+    const T hi = (ihi == 4) ? v[4] : hi4;
+    const T avg = vs_mean2(lo, hi);
     const T med = (ilo == ihi) ? hi : avg;
     return k == 0 ? (T)CUDART_NAN : med;
 }
