@@ -56,6 +56,17 @@ def aoi_struct(aoi_dict, e_resolution, n_resolution, e_size=None, n_size=None, a
     return a
 
 
+class StepGraph:
+    """A captured step of DsmEngine.capture_step."""
+
+    def __init__(self, graph, fused, launches):
+        self.graph, self.fused, self.launches_per_replay = graph, fused, int(launches)
+
+    def replay(self):
+        self.graph.replay()
+        return self.fused
+
+
 class DsmEngine:
     """One AOI on one GPU.  Buffers are allocated once and reused across views."""
 
@@ -124,6 +135,28 @@ class DsmEngine:
         check(lib.vs_views_to_dsm(self.ctx.handle, n, ptrs, Hs, Ws, M.ctypes.data_as(C.POINTER(C.c_double)),
                                   _ptr(self.keygrid), _ptr(out), stack.stride(0), self.simd_lanes,
                                   _ptr(count_nan), C.c_void_p(0), _stream(self.device)), 'vs_views_to_dsm')
+
+    def capture_step(self, depths, mats, stack, fuse=True):
+        """Stages A-C for a fixed set of device buffers as ONE CUDA graph (102 kernel launches + 50 memsets for 50 views): replaying
+        it costs one launch call on the host and removes the per-launch gaps on the device.  The step is run eagerly
+        once first (every lazy allocation inside the library happens there), then captured; the internal streams of
+        vs_views_to_dsm fork from and join into the capturing stream, so the overlap of stage A and stage B is part of
+        the graph.  Returns a StepGraph; `replay()` returns the fused DSM tensor (same storage every time)."""
+        self.set_timing(False)
+
+        def body():
+            self.views_to_dsm(depths, mats, stack)
+            if not fuse:
+                return None
+            return self.median3x3(self.fuse(stack), count_nan=True)
+
+        body()
+        torch.cuda.synchronize(self.device)
+        n0 = self.launch_count()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            fused = body()
+        return StepGraph(graph, fused, self.launch_count() - n0)
 
     def set_exchange(self, ex):
         """Enable (a _native.vs_exchange) or disable (None) the peer stores of stage B (distributed.PeerExchange)."""
