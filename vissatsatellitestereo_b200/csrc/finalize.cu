@@ -40,7 +40,7 @@ __device__ __forceinline__ void write_nan_tile(float* __restrict__ blur_out, T* 
 }
 
 template <typename Key, typename Sink>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, sizeof(Key) == 4 ? 5 : 1)   // float32 keys: 48 registers, 5 CTAs per SM
 k_grid_finalize(const Key* __restrict__ keygrid, int W, int H, typename KeyTraits<Key>::value_t* __restrict__ filled_out,
                 float* __restrict__ blur_out, int simd_cols, unsigned long long* __restrict__ nan_count,
                 const __grid_constant__ Sink sink) {
