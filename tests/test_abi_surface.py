@@ -85,3 +85,37 @@ def test_read_array_matches_reference_golden(golden, tmp_path):
     got = read_array(str(p))
     assert got.dtype == np.float32 and np.array_equal(got, golden['read_array_out'])
     assert np.array_equal(read_array_hw(str(p)), golden['read_array_out'])
+
+
+def test_header_is_plain_c_and_struct_layouts_match_ctypes(native, tmp_path):
+    """include/vissat_b200.h must compile as C (the boundary is a C ABI, no C++ or CUDA types) and the ctypes mirrors of
+    its structs must have the same size and field offsets."""
+    import ctypes as C
+    import shutil
+    import subprocess
+    gcc = shutil.which('gcc')
+    if gcc is None:
+        pytest.skip('no gcc')
+    structs = {'vs_aoi': native.vs_aoi, 'vs_fit_info': native.vs_fit_info, 'vs_exchange': native.vs_exchange}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "vissat_b200.h"', 'int main(void) {']
+    for name, cls in structs.items():
+        lines.append('  printf("{0} size %zu\\n", sizeof({0}));'.format(name))
+        for field, _ in cls._fields_:
+            lines.append('  printf("{0} {1} %zu\\n", offsetof({0}, {1}));'.format(name, field))
+    lines.append('  printf("VS_MAX_RANKS %d\\nVS_IPC_HANDLE_BYTES %d\\nVS_NUM_STATS %d\\n", VS_MAX_RANKS, VS_IPC_HANDLE_BYTES, '
+                 'VS_NUM_STATS);')
+    lines += ['  return 0;', '}']
+    src = tmp_path / 'layout.c'
+    src.write_text('\n'.join(lines) + '\n')
+    exe = str(tmp_path / 'layout')
+    subprocess.run([gcc, '-std=c99', '-Wall', '-Werror', '-pedantic', '-I', os.path.join(REPO, 'include'), str(src), '-o', exe],
+                   check=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout.split('\n')
+    got = {tuple(l.split()[:-1]): int(l.split()[-1]) for l in out if l.strip()}
+    for name, cls in structs.items():
+        assert got[(name, 'size')] == C.sizeof(cls), name
+        for field, _ in cls._fields_:
+            assert got[(name, field)] == getattr(cls, field).offset, (name, field)
+    assert got[('VS_MAX_RANKS',)] == native.VS_MAX_RANKS
+    assert got[('VS_IPC_HANDLE_BYTES',)] == native.VS_IPC_HANDLE_BYTES
+    assert got[('VS_NUM_STATS',)] == native.VS_NUM_STATS
