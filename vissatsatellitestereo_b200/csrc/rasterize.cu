@@ -43,6 +43,14 @@ __device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
 }
+__device__ __forceinline__ void cp_async16_s(unsigned smem_addr, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gmem));
+}
+__device__ __forceinline__ float4 ld_shared_f4(unsigned smem_addr) {
+    float4 r;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(smem_addr));
+    return r;
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 __device__ __forceinline__ void cp_async_wait_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
@@ -183,23 +191,28 @@ k_unproject_scatter(RasterParams p, PolyCoefs pc, const VsExactParams* __restric
     const unsigned n_full = (unsigned)(n_pix / PX);
     const unsigned stride = gridDim.x * blockDim.x;
     const float4* __restrict__ depth4 = reinterpret_cast<const float4*>(depth);
-    int stage = 0;
+    // shared-window addresses of this thread's two slots, computed once (32-bit; a slot is 16 bytes)
+    const unsigned slot0 = (unsigned)__cvta_generic_to_shared(&s_pre[0][threadIdx.x]);
+    const unsigned slot_sum = 2u * slot0 + (unsigned)(sizeof(float4) * kThreads);   // slot0 + slot1
+    unsigned cur_slot = slot0;
     {
         const unsigned first = blockIdx.x * blockDim.x + threadIdx.x;
-        if (simple && first < n_full) cp_async16(&s_pre[0][threadIdx.x], depth4 + first);
+        if (simple && first < n_full) cp_async16_s(slot0, depth4 + first);
         cp_async_commit();
     }
     for (unsigned chunk = blockIdx.x * blockDim.x + threadIdx.x; chunk < n_chunks; chunk += stride) {
         const unsigned base = chunk * PX;
-        if (simple && chunk + stride < n_full) cp_async16(&s_pre[stage ^ 1][threadIdx.x], depth4 + (chunk + stride));
+        const unsigned next_slot = slot_sum - cur_slot;   // the other slot
+        if (simple && chunk + stride < n_full) cp_async16_s(next_slot, depth4 + (chunk + stride));
         cp_async_commit();
         cp_async_wait_but_one();
-        const float4 cur = s_pre[stage][threadIdx.x];
-        stage ^= 1;
+        const float4 cur = ld_shared_f4(cur_slot);
+        cur_slot = next_slot;
         // row = base / W by multiply-shift (magic = ceil(2^48 / W), exact for base < 2^32, W < 2^16)
         const unsigned row0 = (unsigned)(((unsigned long long)base * p.w_magic) >> 48);
         const unsigned col0 = base - row0 * (unsigned)p.W;
-        if (col0 + PX > (unsigned)p.W || (int64_t)base + PX > n_pix) {   // straddles rows / ragged tail (rare)
+        // straddles rows / ragged tail (rare).  With a pitch that is a multiple of PX only the last, partial chunk can.
+        if (simple ? (chunk >= n_full) : (col0 + PX > (unsigned)p.W || (int64_t)base + PX > n_pix)) {
             scatter_chunk_generic<D, D64>(p, pc, ex, depth, base, n_pix, keygrid, height_map, audit, cnt);
             continue;
         }
