@@ -185,15 +185,17 @@ __device__ __forceinline__ unsigned blur_tile(const float* __restrict__ s_fill, 
                 const float4 v4 = make_float4(res[j][0], res[j][1], res[j][2], res[j][3]);
                 *reinterpret_cast<float4*>(o) = v4;
                 sink.store4(y_g, gx, W, v4);
+                if (tile_has_nan) {   // block-uniform; a tile without a NaN going in has none coming out
 #pragma unroll
-                for (int x = 0; x < 4; ++x) n_nan += (res[j][x] != res[j][x]);
+                    for (int x = 0; x < 4; ++x) n_nan += (res[j][x] != res[j][x]);
+                }
             } else {
 #pragma unroll
                 for (int x = 0; x < 4; ++x)
                     if (gx + x < W) {
                         o[x] = res[j][x];
                         sink.store1(y_g, gx + x, W, res[j][x]);
-                        n_nan += (res[j][x] != res[j][x]);
+                        n_nan += (tile_has_nan && res[j][x] != res[j][x]);
                     }
             }
         }
