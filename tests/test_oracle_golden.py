@@ -1,6 +1,5 @@
 """The oracle against vectors produced by running the reference itself (tests/golden/make_golden.py)."""
 import json
-import os
 
 import numpy as np
 import pytest

@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from oracle import geodesy, pipeline as op
+from oracle import geodesy
 from vissatsatellitestereo_b200 import synthetic as S
 
 

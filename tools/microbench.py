@@ -3,9 +3,7 @@
 what: fuse k1 k2 k4 (default: all)."""
 import os
 import sys
-import time
 
-import numpy as np
 import torch
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

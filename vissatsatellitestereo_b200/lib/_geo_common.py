@@ -1,5 +1,4 @@
 """Shared plumbing for the converter modules: host numpy arrays -> device float64 -> exact CUDA chain -> host."""
-import ctypes as C
 
 import numpy as np
 import torch
