@@ -119,6 +119,18 @@ def test_rowband_exchange_world2_gloo(n_rows, counts):
     assert dict(out) == {0: True, 1: True}
 
 
+@pytest.mark.parametrize('world,n_rows,counts', [(3, 10, [3, 2, 2]), (4, 3, [1, 2, 0, 1])])
+def test_rowband_exchange_more_ranks_gloo(world, n_rows, counts):
+    """Uneven view blocks, row counts that do not divide by the world size, middle ranks with two halo neighbours, and
+    fewer rows than ranks (an empty band)."""
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_exchange_worker, args=(world, port, n_rows, 7, counts, out), nprocs=world, join=True)
+    assert dict(out) == {r: True for r in range(world)}
+
+
 def test_bind_to_gpu_numa_node_with_fake_sysfs(tmp_path, monkeypatch):
     """hostbind: affinity follows <sysfs>/bus/pci/devices/<bus>/numa_node -> node<N>/cpulist; unknown -> unchanged."""
     import os
