@@ -48,6 +48,18 @@ def test_no_gpu_means_loud_failure(native):
         engine.require_cuda()
 
 
+def test_bench_without_gpu_fails_loudly_and_prints_no_number():
+    """bench.py's own arm must not fall back to anything when there is no CUDA device: non-zero exit, no JSON line."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    r = subprocess.run([sys.executable, os.path.join(REPO, 'bench.py'), '--steps', '1', '--warmup', '0'],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0
+    assert 'no CUDA device' in r.stderr
+    assert not any(line.startswith('{') for line in r.stdout.splitlines())
+
+
 def test_product_never_imports_oracle():
     pkg = os.path.join(REPO, 'vissatsatellitestereo_b200')
     for root, _, files in os.walk(pkg):
