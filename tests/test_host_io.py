@@ -157,3 +157,49 @@ def test_bind_to_gpu_numa_node_with_fake_sysfs(tmp_path, monkeypatch):
         assert os.sched_getaffinity(0) == {allowed[0]}
     finally:
         os.sched_setaffinity(0, set(allowed))
+
+
+def test_convert_depth_maps_read_ahead_is_bounded_and_ordered(tmp_path, monkeypatch):
+    """Host logic of aggregate_2p5d_util.convert_depth_maps (:131-146) with the GPU parts stubbed: every matching item
+    is processed once, in sorted order; other files are passed through to the worker (which logs and skips them); at
+    most 2 * n_io depth maps are loaded ahead of the consumer; stale output is wiped (:127-128)."""
+    import threading
+    from vissatsatellitestereo_b200 import aggregate_2p5d_util as U
+    work = tmp_path / 'work'
+    depth_dir = work / 'colmap/mvs/stereo/depth_maps'
+    depth_dir.mkdir(parents=True)
+    names = ['{:04d}.png.geometric.bin'.format(i) for i in range(23)] + ['0003.png.photometric.bin', 'notes.geometric.txt']
+    for n in names:
+        (depth_dir / n).write_bytes(b'x')
+    out_dir = work / 'colmap/mvs/dsm'
+    (out_dir / 'dsm_tif').mkdir(parents=True)
+    (out_dir / 'dsm_tif/stale.tif').write_bytes(b'old')
+    lock = threading.Lock()
+    live = {'loaded': 0, 'max': 0}
+    seen = []
+
+    def fake_read(path):
+        with lock:
+            live['loaded'] += 1
+            live['max'] = max(live['max'], live['loaded'])
+        return os.path.basename(path)
+
+    def fake_worker(work_dir, out, item, depth_type, _state=None):
+        if _state['depth_host'] is not None:
+            assert _state['depth_host'] == item           # the prefetched array belongs to this item
+            with lock:
+                live['loaded'] -= 1
+        seen.append(item)
+        return ('dsm', 0, item) if item.endswith('.bin') else None
+
+    monkeypatch.setattr(U, 'read_array', fake_read)
+    monkeypatch.setattr(U, 'convert_depth_map_worker', fake_worker)
+    monkeypatch.setattr(U, '_make_engine', lambda wd: ('engine', {'aoi': 1}))
+    monkeypatch.setattr(U, 'load_inv_proj_mats', lambda d: {})
+    U.convert_depth_maps(str(work), str(out_dir), 'geometric', max_processes=3)
+    want = sorted(n for n in names if 'geometric' in n)
+    assert seen == want
+    assert live['max'] <= 2 * 3 + 1 and live['loaded'] == 0
+    assert not (out_dir / 'dsm_tif/stale.tif').exists()
+    res = U._RESULTS.pop(os.path.abspath(str(out_dir)))
+    assert [v[2] for v in res['views']] == [n for n in want if n.endswith('.bin')] and res['world'] == 1

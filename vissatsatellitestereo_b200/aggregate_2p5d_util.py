@@ -6,6 +6,7 @@ numpy/pymap3d/pyproj; here one process owns the GPU, `max_processes` only bounds
 contexts do not survive fork), and every view goes through libvissat_b200 (stage A + B).  Under torchrun the
 sorted view list is split into contiguous blocks, one per rank.
 """
+import collections
 import logging
 import os
 import shutil
@@ -136,14 +137,26 @@ def convert_depth_maps(work_dir, out_dir, depth_type, max_processes=-1):
     results = []
     n_io = max(1, min(max_processes, len(my_items), 8))
     with ThreadPoolExecutor(n_io) as pool:
-        # host threads read ahead; the GPU work itself is serialised on this process's stream
+        # host threads read ahead (at most 2 * n_io depth maps wait in host memory); the GPU work itself is serialised
+        # on this process's stream
         def load(item):
             if item.rfind('.{}.bin'.format(depth_type)) == -1:
                 return None
             return read_array(os.path.join(depth_dir, item))
-        futures = [pool.submit(load, item) for item in my_items]
-        for item, fut in zip(my_items, futures):
+        todo = iter(my_items)
+        pending = collections.deque()
+
+        def refill():
+            while len(pending) < 2 * n_io:
+                nxt = next(todo, None)
+                if nxt is None:
+                    return
+                pending.append((nxt, pool.submit(load, nxt)))
+        refill()
+        while pending:
+            item, fut = pending.popleft()
             state['depth_host'] = fut.result()
+            refill()
             r = convert_depth_map_worker(work_dir, out_dir, item, depth_type, _state=state)
             if r is not None:
                 results.append(r)
