@@ -203,3 +203,82 @@ def test_convert_depth_maps_read_ahead_is_bounded_and_ordered(tmp_path, monkeypa
     assert not (out_dir / 'dsm_tif/stale.tif').exists()
     res = U._RESULTS.pop(os.path.abspath(str(out_dir)))
     assert [v[2] for v in res['views']] == [n for n in want if n.endswith('.bin')] and res['world'] == 1
+
+
+def _write_tiled_tif(path, a, tile, bo='<', deflate=False):
+    """Minimal tiled float32 TIFF (classic, one IFD) for the reader test."""
+    import struct
+    import zlib
+    h, w = a.shape
+    tl, tw = tile
+    tiles = []
+    for r0 in range(0, h, tl):
+        for c0 in range(0, w, tw):
+            t = np.zeros((tl, tw), dtype=np.float32)
+            blk = a[r0:r0 + tl, c0:c0 + tw]
+            t[:blk.shape[0], :blk.shape[1]] = blk
+            raw = t.astype(bo + 'f4').tobytes()
+            tiles.append(zlib.compress(raw) if deflate else raw)
+    n = len(tiles)
+    entries = [(256, 4, [w]), (257, 4, [h]), (258, 3, [32]), (259, 3, [8 if deflate else 1]), (262, 3, [1]), (277, 3, [1]),
+               (322, 4, [tw]), (323, 4, [tl]), (339, 3, [3])]
+    header = 8
+    ifd_size = 2 + 12 * (len(entries) + 2) + 4
+    arrays_off = header + ifd_size
+    data_off = arrays_off + 8 * n
+    offs, pos = [], data_off
+    for t in tiles:
+        offs.append(pos)
+        pos += len(t)
+    entries += [(324, 4, offs), (325, 4, [len(t) for t in tiles])]
+    entries.sort()
+    with open(path, 'wb') as fp:
+        fp.write((b'II' if bo == '<' else b'MM') + struct.pack(bo + 'HI', 42, header))
+        fp.write(struct.pack(bo + 'H', len(entries)))
+        arr_pos = arrays_off
+        blobs = b''
+        for tag, typ, vals in entries:
+            fmt = {3: 'H', 4: 'I'}[typ]
+            payload = struct.pack(bo + str(len(vals)) + fmt, *vals)
+            if len(payload) <= 4:
+                fp.write(struct.pack(bo + 'HHI', tag, typ, len(vals)) + payload.ljust(4, b'\0'))
+            else:
+                fp.write(struct.pack(bo + 'HHII', tag, typ, len(vals), arr_pos))
+                blobs += payload
+                arr_pos += len(payload)
+        fp.write(struct.pack(bo + 'I', 0))
+        assert fp.tell() == arrays_off and len(blobs) == 8 * n
+        fp.write(blobs)
+        for t in tiles:
+            fp.write(t)
+
+
+def test_tif_reader_takes_compressed_predicted_and_tiled_files(tmp_path):
+    """lib/dsm_util.read_dsm_tif on files other writers produce: Pillow/libtiff strips with LZW / Deflate / PackBits and
+    predictors 1-3 (an independent encoder), and hand-written tiled files of both byte orders."""
+    from vissatsatellitestereo_b200.lib.dsm_util import read_dsm_tif
+    Image = pytest.importorskip('PIL.Image')
+    rng = np.random.default_rng(7)
+    a = (rng.normal(size=(70, 53)) * 100).astype(np.float32)
+    a[3:9, 4:20] = 12.5                                   # runs, so that PackBits/LZW have something to find
+    im = Image.fromarray(a, mode='F')
+    for comp in (None, 'tiff_lzw', 'tiff_adobe_deflate', 'packbits'):
+        for pred in (None, 2, 3):
+            path = str(tmp_path / 'p_{}_{}.tif'.format(comp, pred))
+            kw = {}
+            if comp:
+                kw['compression'] = comp
+            if pred:
+                kw['tiffinfo'] = {317: pred}
+            im.save(path, **kw)
+            got, meta = read_dsm_tif(path)
+            assert np.array_equal(got, a), (comp, pred)
+            assert (meta['img_height'], meta['img_width']) == a.shape and meta['zone_number'] is None
+    for bo in ('<', '>'):
+        for deflate in (False, True):
+            path = str(tmp_path / 'tiled_{}_{}.tif'.format('le' if bo == '<' else 'be', int(deflate)))
+            _write_tiled_tif(path, a, (32, 16), bo=bo, deflate=deflate)
+            if not (bo == '>' and deflate):      # (Pillow mis-swaps big-endian data that went through its libtiff decoder)
+                assert np.array_equal(np.array(Image.open(path)), a)      # the test writer itself is sane
+            got, _ = read_dsm_tif(path)
+            assert np.array_equal(got, a), (bo, deflate)

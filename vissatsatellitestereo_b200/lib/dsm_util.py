@@ -9,11 +9,14 @@ Same function names, arguments and return values:
 Files written: baseline little-endian TIFF, one float32 band, uncompressed strips, GeoTIFF keys for
 EPSG:326xx/327xx (WGS 84 / UTM zone NN N|S), ModelPixelScale + ModelTiepoint equivalent to the reference's
 geotransform (ul_e, res, 0, ul_n, 0, -res), RasterPixelIsArea (the reference's AREA_OR_POINT=Area) and the
-GDAL_NODATA tag, so GDAL/QGIS read them like the reference's outputs.  The reader handles this subset
-(uncompressed, strip-organised, single-band float32, either byte order), which is what both writers produce.
+GDAL_NODATA tag, so GDAL/QGIS read them like the reference's outputs.  The reader takes single-band float32 classic
+TIFFs of either byte order, organised in strips or tiles, uncompressed or with the compressions GDAL users commonly
+choose (Deflate, LZW, PackBits) and predictors 1, 2 and 3 -- so per-view DSMs written by the reference itself (GDAL
+defaults or creation options) can be fed to the fusion.  BigTIFF and multi-band files are rejected.
 """
 import os
 import struct
+import zlib
 
 import numpy as np
 
@@ -21,6 +24,7 @@ import numpy as np
 _T_WIDTH, _T_LENGTH, _T_BITS, _T_COMPRESSION, _T_PHOTOMETRIC = 256, 257, 258, 259, 262
 _T_STRIP_OFFSETS, _T_SPP, _T_ROWS_PER_STRIP, _T_STRIP_BYTES, _T_PLANAR, _T_SAMPLE_FORMAT = 273, 277, 278, 279, 284, 339
 _T_PIXEL_SCALE, _T_TIEPOINT, _T_TRANSFORM, _T_GEOKEYS, _T_GEO_DOUBLES, _T_GEO_ASCII = 33550, 33922, 34264, 34735, 34736, 34737
+_T_PREDICTOR, _T_TILE_WIDTH, _T_TILE_LENGTH, _T_TILE_OFFSETS, _T_TILE_BYTES = 317, 322, 323, 324, 325
 _T_GDAL_METADATA, _T_GDAL_NODATA = 42112, 42113
 _TYPE_SIZE = {1: 1, 2: 1, 3: 2, 4: 4, 5: 8, 6: 1, 7: 1, 8: 2, 9: 4, 10: 8, 11: 4, 12: 8, 16: 8}
 _TYPE_FMT = {1: 'B', 2: 'c', 3: 'H', 4: 'I', 6: 'b', 8: 'h', 9: 'i', 11: 'f', 12: 'd', 16: 'Q'}
@@ -189,6 +193,89 @@ def _read_ifd(buf, bo):
     return tags
 
 
+def _unpackbits(data):
+    out = bytearray()
+    i, n = 0, len(data)
+    while i < n:
+        c = data[i]
+        i += 1
+        if c < 128:
+            out += data[i:i + c + 1]
+            i += c + 1
+        elif c > 128:
+            out += data[i:i + 1] * (257 - c)
+            i += 1
+    return bytes(out)
+
+
+def _unlzw(data):
+    """TIFF LZW (MSB-first codes of 9..12 bits, ClearCode 256, EndOfInformation 257, 'early change')."""
+    out = bytearray()
+    table, width, prev = None, 9, None
+    bitbuf = nbits = pos = 0
+    n = len(data)
+    while True:
+        while nbits < width:
+            if pos >= n:
+                return bytes(out)
+            bitbuf = ((bitbuf << 8) | data[pos]) & 0xFFFFFF
+            pos += 1
+            nbits += 8
+        code = (bitbuf >> (nbits - width)) & ((1 << width) - 1)
+        nbits -= width
+        if code == 257:
+            return bytes(out)
+        if code == 256:
+            table = [bytes((i,)) for i in range(256)] + [b'', b'']
+            width, prev = 9, None
+            continue
+        if table is None:
+            raise ValueError('LZW stream does not start with a clear code')
+        if prev is None:
+            entry = table[code]
+        elif code < len(table):
+            entry = table[code]
+            table.append(prev + entry[:1])
+        else:
+            entry = prev + prev[:1]
+            table.append(entry)
+        out += entry
+        prev = entry
+        if len(table) >= (1 << width) - 1 and width < 12:
+            width += 1
+
+
+def _decode_chunk(raw, compression, predictor, rows, cols, bo):
+    """One strip or tile -> float32 (rows, cols)."""
+    if compression == 1:
+        data = bytes(raw)
+    elif compression in (8, 32946):
+        data = zlib.decompress(bytes(raw))
+    elif compression == 5:
+        data = _unlzw(bytes(raw))
+    elif compression == 32773:
+        data = _unpackbits(bytes(raw))
+    else:
+        raise ValueError('TIFF compression {} is not supported'.format(compression))
+    if compression not in (5, 8, 32946):
+        predictor = 1         # libtiff applies the Predictor tag only inside the LZW / Deflate codecs
+    need = rows * cols * 4
+    if len(data) < need:
+        raise ValueError('strip/tile data is short: {} < {} bytes'.format(len(data), need))
+    if predictor == 1:
+        return np.frombuffer(data, dtype=bo + 'f4', count=rows * cols).reshape(rows, cols)
+    if predictor == 2:        # horizontal differencing of the 32-bit words
+        u = np.frombuffer(data, dtype=bo + 'u4', count=rows * cols).reshape(rows, cols)
+        u = np.cumsum(u, axis=1, dtype=np.uint64).astype(np.uint32)
+        return u.view(np.float32)
+    if predictor == 3:        # floating-point predictor: byte planes (most significant first), differenced bytewise
+        b = np.frombuffer(data, dtype=np.uint8, count=need).reshape(rows, cols * 4)
+        b = np.cumsum(b, axis=1, dtype=np.uint64).astype(np.uint8)
+        be = np.ascontiguousarray(b.reshape(rows, 4, cols).transpose(0, 2, 1))      # (rows, cols, 4) big-endian bytes
+        return be.view('>f4').reshape(rows, cols).astype(np.float32)
+    raise ValueError('TIFF predictor {} is not supported'.format(predictor))
+
+
 def read_dsm_tif(file):
     assert (os.path.exists(file))
     with open(file, 'rb') as fp:
@@ -200,18 +287,28 @@ def read_dsm_tif(file):
     width, height = tags[_T_WIDTH][0], tags[_T_LENGTH][0]
     assert (tags.get(_T_SPP, [1])[0] == 1)     # dsm is only one band (:59)
     assert (tags.get(_T_BITS, [0])[0] == 32 and tags.get(_T_SAMPLE_FORMAT, [1])[0] == 3)    # float32 (:62-63)
-    if tags.get(_T_COMPRESSION, [1])[0] != 1:
-        raise ValueError('compressed TIFFs are not supported by this reader: {}'.format(file))
+    compression = tags.get(_T_COMPRESSION, [1])[0]
+    predictor = tags.get(_T_PREDICTOR, [1])[0]
+    if tags.get(_T_PLANAR, [1])[0] != 1:
+        raise ValueError('planar configuration 2 is not supported: {}'.format(file))
     image = np.zeros((height, width), dtype=np.float32)
-    rps = tags.get(_T_ROWS_PER_STRIP, [height])[0]
-    flat = image.reshape(-1)
-    pos = 0
-    for off, nbytes in zip(tags[_T_STRIP_OFFSETS], tags[_T_STRIP_BYTES]):
-        n = nbytes // 4
-        flat[pos:pos + n] = np.frombuffer(buf, dtype=bo + 'f4', count=n, offset=off)
-        pos += n
-    assert pos == width * height, 'strip data does not cover the image'
-    del rps
+    if _T_TILE_OFFSETS in tags:
+        tw, tl = tags[_T_TILE_WIDTH][0], tags[_T_TILE_LENGTH][0]
+        across = (width + tw - 1) // tw
+        for i, (off, nbytes) in enumerate(zip(tags[_T_TILE_OFFSETS], tags[_T_TILE_BYTES])):
+            tile = _decode_chunk(buf[off:off + nbytes], compression, predictor, tl, tw, bo)
+            r0, c0 = (i // across) * tl, (i % across) * tw
+            if r0 >= height:
+                break
+            image[r0:r0 + tl, c0:c0 + tw] = tile[:height - r0, :width - c0]       # edge tiles are padded
+    else:
+        rps = min(tags.get(_T_ROWS_PER_STRIP, [height])[0], height)
+        for i, (off, nbytes) in enumerate(zip(tags[_T_STRIP_OFFSETS], tags[_T_STRIP_BYTES])):
+            r0 = i * rps
+            rows = min(rps, height - r0)
+            if rows <= 0:
+                break
+            image[r0:r0 + rows] = _decode_chunk(buf[off:off + nbytes], compression, predictor, rows, width, bo)
 
     nodata = None
     if _T_GDAL_NODATA in tags:
@@ -244,7 +341,8 @@ def read_dsm_tif(file):
                 elif 32701 <= epsg <= 32760:
                     proj = _utm_wkt(epsg - 32700, 'S')
     meta = {'AREA_OR_POINT': 'Area'} if keys and 1025 in keys[4::4] else {}
-    zone_number, hemisphere = parse_proj_str(proj)
+    # a TIFF without GeoTIFF keys has no projection string (GDAL would return ''; parse_proj_str needs a UTM name)
+    zone_number, hemisphere = parse_proj_str(proj) if proj else (None, None)
     # return a meta dict (:76-99)
     meta_dict = {
         'geo': geo,
