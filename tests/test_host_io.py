@@ -282,3 +282,47 @@ def test_tif_reader_takes_compressed_predicted_and_tiled_files(tmp_path):
                 assert np.array_equal(np.array(Image.open(path)), a)      # the test writer itself is sane
             got, _ = read_dsm_tif(path)
             assert np.array_equal(got, a), (bo, deflate)
+
+
+def test_ply_reader_takes_colmap_style_and_meshes(tmp_path):
+    """ply2np on what the pipeline feeds it: COLMAP's fused.ply (x y z nx ny nz red green blue, binary little endian)
+    and, for robustness, big-endian data, an ASCII file and a mesh whose face element follows the vertices."""
+    from vissatsatellitestereo_b200.lib.ply_np_converter import ply2np
+    rng = np.random.default_rng(3)
+    n = 17
+    xyz = rng.normal(size=(n, 3)).astype(np.float32)
+    nrm = rng.normal(size=(n, 3)).astype(np.float32)
+    rgb = rng.integers(0, 256, size=(n, 3)).astype(np.uint8)
+    for bo, fmt in (('<', 'binary_little_endian'), ('>', 'binary_big_endian')):
+        dt = np.dtype([(k, bo + 'f4') for k in ('x', 'y', 'z', 'nx', 'ny', 'nz')] + [(k, 'u1') for k in ('red', 'green', 'blue')])
+        rec = np.empty(n, dtype=dt)
+        for i, k in enumerate(('x', 'y', 'z')):
+            rec[k] = xyz[:, i]
+        for i, k in enumerate(('nx', 'ny', 'nz')):
+            rec[k] = nrm[:, i]
+        for i, k in enumerate(('red', 'green', 'blue')):
+            rec[k] = rgb[:, i]
+        header = ['ply', 'format {} 1.0'.format(fmt), 'comment made by a test', 'element vertex {}'.format(n)] + \
+                 ['property float {}'.format(k) for k in ('x', 'y', 'z', 'nx', 'ny', 'nz')] + \
+                 ['property uchar {}'.format(k) for k in ('red', 'green', 'blue')] + \
+                 ['element face 2', 'property list uchar int vertex_indices', 'end_header']
+        path = str(tmp_path / (fmt + '.ply'))
+        with open(path, 'wb') as fp:
+            fp.write(('\n'.join(header) + '\n').encode('ascii'))
+            fp.write(rec.tobytes())
+            fp.write(np.array([3], np.uint8).tobytes() + np.array([0, 1, 2], bo + 'i4').tobytes())
+            fp.write(np.array([3], np.uint8).tobytes() + np.array([2, 1, 3], bo + 'i4').tobytes())
+        data, color, comments = ply2np(path)
+        assert np.array_equal(data, xyz) and np.array_equal(color, rgb) and comments == ['made by a test']
+    path = str(tmp_path / 'ascii.ply')
+    with open(path, 'w') as fp:
+        fp.write('ply\nformat ascii 1.0\nelement vertex 2\nproperty double x\nproperty double y\nproperty double z\n'
+                 'property uint8 red\nproperty uint8 green\nproperty uint8 blue\nelement face 1\n'
+                 'property list uchar int vertex_indices\nend_header\n1.5 2.5 -3 1 2 3\n4 5 6.25 255 0 7\n3 0 1 1\n')
+    data, color, comments = ply2np(path)
+    assert np.array_equal(data, [[1.5, 2.5, -3], [4, 5, 6.25]]) and np.array_equal(color, [[1, 2, 3], [255, 0, 7]])
+    assert comments is None
+    with open(str(tmp_path / 'bad.ply'), 'w') as fp:
+        fp.write('plx\n')
+    with pytest.raises(ValueError):
+        ply2np(str(tmp_path / 'bad.ply'))

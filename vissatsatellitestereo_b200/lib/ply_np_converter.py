@@ -36,29 +36,51 @@ def np2ply(vertex, out_ply, color=None, comments=None, text=False, use_double=Fa
             fp.write(data.tobytes())
 
 
+_PLY_TYPES = {'char': 'i1', 'int8': 'i1', 'uchar': 'u1', 'uint8': 'u1', 'short': 'i2', 'int16': 'i2', 'ushort': 'u2',
+              'uint16': 'u2', 'int': 'i4', 'int32': 'i4', 'uint': 'u4', 'uint32': 'u4', 'float': 'f4', 'float32': 'f4',
+              'double': 'f8', 'float64': 'f8'}
+
+
 def ply2np(in_ply):
+    """(N,3) xyz, (N,3) uint8 colour or None, comments or None -- the return of lib/ply_np_converter.py:71-92.  Reads the
+    `vertex` element (any scalar properties, e.g. COLMAP's x y z nx ny nz red green blue) of an ASCII or binary PLY;
+    the vertex element must come first (it does in every writer of this pipeline); later elements (faces) are ignored."""
     with open(in_ply, 'rb') as fp:
-        fmt, n, props, comments = None, 0, [], []
+        fmt, n, props, comments, element = None, 0, [], [], None
+        if fp.readline().strip() != b'ply':
+            raise ValueError('not a PLY file: {}'.format(in_ply))
         while True:
-            line = fp.readline().decode('ascii').strip()
+            raw = fp.readline()
+            if not raw:
+                raise ValueError('PLY header has no end_header: {}'.format(in_ply))
+            line = raw.decode('ascii', 'replace').strip()
             if line.startswith('format'):
                 fmt = line.split()[1]
             elif line.startswith('comment'):
                 comments.append(line[len('comment '):])
-            elif line.startswith('element vertex'):
-                n = int(line.split()[2])
-            elif line.startswith('property'):
-                _, typ, name = line.split()
-                props.append((name, {'float': 'f4', 'double': 'f8', 'uchar': 'u1', 'float32': 'f4', 'float64': 'f8',
-                                     'uint8': 'u1'}[typ]))
+            elif line.startswith('element'):
+                element = line.split()[1]
+                if element == 'vertex':
+                    if props:
+                        raise ValueError('two vertex elements')
+                    n = int(line.split()[2])
+                elif not props and int(line.split()[2]) > 0:
+                    raise ValueError('PLY element {} precedes the vertices: {}'.format(element, in_ply))
+            elif line.startswith('property') and element == 'vertex':
+                tok = line.split()
+                if tok[1] == 'list':
+                    raise ValueError('list property in the vertex element: {}'.format(in_ply))
+                props.append((tok[2], _PLY_TYPES[tok[1]]))
             elif line == 'end_header':
                 break
         if fmt == 'ascii':
-            raw = np.loadtxt(fp, ndmin=2)
+            rows = [fp.readline().split() for _ in range(n)]
+            raw = np.array(rows, dtype=np.float64).reshape(n, len(props))
             cols = {name: raw[:, i] for i, (name, _) in enumerate(props)}
         else:
             bo = '<' if fmt == 'binary_little_endian' else '>'
-            arr = np.frombuffer(fp.read(), dtype=[(nm, bo + t if t != 'u1' else t) for nm, t in props], count=n)
+            dt = np.dtype([(nm, t if t[1] == '1' else bo + t) for nm, t in props])
+            arr = np.frombuffer(fp.read(n * dt.itemsize), dtype=dt, count=n)
             cols = {name: arr[name] for name, _ in props}
     data = np.stack([cols['x'], cols['y'], cols['z']], axis=1) if 'x' in cols else None
     color = np.stack([cols['red'], cols['green'], cols['blue']], axis=1).astype(np.uint8) if 'red' in cols else None
