@@ -326,3 +326,24 @@ def test_ply_reader_takes_colmap_style_and_meshes(tmp_path):
         fp.write('plx\n')
     with pytest.raises(ValueError):
         ply2np(str(tmp_path / 'bad.ply'))
+
+
+def test_native_band_split_equals_numpy_array_split():
+    """The row bands the stage-B peer stores use (exchange.cu: vs_band_rows, a host function of the shipped library)
+    must be the ones distributed.row_bands (numpy.array_split) hands to the fusion, for every grid height and rank count."""
+    import ctypes as C
+    from vissatsatellitestereo_b200 import _native, distributed as D
+    try:
+        fn = getattr(_native.lib, '_Z12vs_band_rowsiiPi')
+    except AttributeError:
+        pytest.skip('internal symbol not exported by this build')
+    fn.restype, fn.argtypes = None, [C.c_int, C.c_int, C.POINTER(C.c_int)]
+    for n in range(1, _native.VS_MAX_RANKS + 1):
+        for H in list(range(1, 70)) + [257, 2048, 8191]:
+            row0 = (C.c_int * (n + 1))()
+            fn(H, n, row0)
+            assert row0[0] == 0 and row0[n] == H
+            for j, (a, b) in enumerate(D.row_bands(H, n)):
+                assert b - a == row0[j + 1] - row0[j]
+                if b > a:
+                    assert (a, b) == (row0[j], row0[j + 1])
