@@ -92,6 +92,10 @@ int vs_ctx_destroy(vs_ctx* ctx);
  * max_degree: 3..5; 0 forces the exact chain for every point.  info may be NULL. */
 int vs_set_aoi(vs_ctx* ctx, const vs_aoi* aoi, int max_degree, vs_fit_info* info);
 int vs_set_ambiguity_eps(vs_ctx* ctx, double eps_cells); /* default 1e-7 */
+/* Diagnostics: evaluate the validated polynomial on n ENU points (HOST arrays; enu = n rows of e, n, u) with the
+ * arithmetic K1 uses -> fractional column, fractional row (lib/proj_to_grid.py:42-43 before the floor) and altitude.
+ * tests/test_geodesy_pin.py compares it with an independent 50-digit evaluation of the map. */
+int vs_fit_eval(vs_ctx* ctx, const double* enu, int64_t n, double* colf, double* rowf, double* alt);
 
 /* ---- stage A: depth map -> max-height key grid ---------------------------------------------------------
  * Replaces aggregate_2p5d_util.py:75-98 (NaN-ing, pixel grid, M*[col,row,1,depth], perspective divide,

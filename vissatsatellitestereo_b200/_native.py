@@ -58,6 +58,7 @@ SIGNATURES = {
     'vs_ctx_destroy': (C.c_int, [_vp]),
     'vs_set_aoi': (C.c_int, [_vp, C.POINTER(vs_aoi), C.c_int, C.POINTER(vs_fit_info)]),
     'vs_set_ambiguity_eps': (C.c_int, [_vp, _dbl]),
+    'vs_fit_eval': (C.c_int, [_vp, C.POINTER(_dbl), _i64, C.POINTER(_dbl), C.POINTER(_dbl), C.POINTER(_dbl)]),
     'vs_unproject_rasterize': (C.c_int, [_vp, _vp, _i32, _i32, C.POINTER(_dbl), _vp, C.c_int, _vp, _vp, _vp]),
     'vs_keygrid_clear': (C.c_int, [_vp, _vp, _i64, C.c_int, _vp]),
     'vs_points_rasterize': (C.c_int, [_vp, _vp, _i64, _dbl, _dbl, _dbl, _dbl, _i32, _i32, _vp, C.c_int, _vp, _vp]),

@@ -326,3 +326,28 @@ extern "C" int vs_set_aoi(vs_ctx* ctx, const vs_aoi* aoi, int max_degree, vs_fit
     if (info) *info = ctx->fit;
     return VS_OK;
 }
+
+// Evaluate the activated polynomial on explicit ENU points (host arrays) exactly as K1 evaluates it (same Horner
+// order, same float64/float32 split).  Diagnostics: lets a test compare the fit with an independent exact map.
+extern "C" int vs_fit_eval(vs_ctx* ctx, const double* enu, int64_t n, double* colf, double* rowf, double* alt) {
+    VS_REQUIRE(ctx != nullptr, "vs_fit_eval: NULL context");
+    if (!ctx->aoi_set || ctx->poly.degree == 0) {
+        vs_set_error("vs_fit_eval: no validated polynomial (vs_set_aoi not called, or exact mode)");
+        return VS_ERR_STATE;
+    }
+    VS_REQUIRE(n >= 0 && (n == 0 || (enu && colf && rowf && alt)), "vs_fit_eval: NULL argument");
+    const VsPoly& P = ctx->poly;
+    double* outs[3] = {colf, rowf, alt};
+    for (int64_t i = 0; i < n; ++i) {
+        const double u = (enu[3 * i] - P.center[0]) * P.inv_half[0];
+        const double v = (enu[3 * i + 1] - P.center[1]) * P.inv_half[1];
+        const double w = (enu[3 * i + 2] - P.center[2]) * P.inv_half[2];
+        for (int o = 0; o < 3; ++o) {
+            const double hi = P.d64 ? (double)eval_poly_host_f32(P.degree, P.coefR[o], (float)u, (float)v, (float)w) : 0.0;
+            if (P.d64 == 1) outs[o][i] = vs_poly_eval<1>(P.coefLo[o], u, v, w) + hi;
+            else if (P.d64 == 2) outs[o][i] = vs_poly_eval<2>(P.coefLo[o], u, v, w) + hi;
+            else outs[o][i] = eval_poly_host(P.degree, P.coef[o], u, v, w);
+        }
+    }
+    return VS_OK;
+}

@@ -276,6 +276,17 @@ class DsmEngine:
         cur.synchronize()
         return stack, fused
 
+    def eval_poly(self, enu):
+        """Diagnostics (vs_fit_eval): the validated ENU -> (fractional col, fractional row, altitude) polynomial of this
+        AOI on (n, 3) host points, in K1's arithmetic."""
+        pts = np.ascontiguousarray(np.asarray(enu, dtype=np.float64).reshape(-1, 3))
+        n = pts.shape[0]
+        out = [np.empty(n, dtype=np.float64) for _ in range(3)]
+        dp = C.POINTER(C.c_double)
+        check(lib.vs_fit_eval(self.ctx.handle, pts.ctypes.data_as(dp), n, *[o.ctypes.data_as(dp) for o in out]),
+              'vs_fit_eval')
+        return tuple(out)
+
     def launch_count(self):
         return self.ctx.launch_count()
 
