@@ -251,8 +251,11 @@ def test_end_to_end_vs_reference_golden(golden, eng_mod, lanes, case):
     diff[np.isnan(diff)] = 0
     bad = diff > HEIGHT_TOL
     # a >1 mm difference is only acceptable where the reference's own strict MAD test sits on a float32 tie
+    print('[end-to-end {}] fused cells > {} m: {} of {} (fragile mask: {} cells); ambiguous points: {}'.format(
+        case, HEIGHT_TOL, int(bad.sum()), bad.size, int(fragile.sum()), n_amb))
     assert not np.any(bad & ~fragile), 'unexplained cells: {}'.format(np.argwhere(bad & ~fragile)[:10])
-    assert bad.mean() < 0.01
+    assert bad.sum() <= fragile.sum()
+    assert bad.sum() <= max(2, 1e-4 * bad.size), int(bad.sum())      # absolute cap on the escape hatch
 
 
 def test_captured_step_replays_bit_identically(golden, eng_mod, lanes):

@@ -67,7 +67,11 @@ def test_run_fuse_file_outputs(golden, tmp_path, case, res):
     fragile = cv2.dilate(fragile.astype(np.uint8), np.ones((3, 3), np.uint8)).astype(bool)
     diff = np.abs(fused.astype(np.float64) - want.astype(np.float64))
     diff[np.isnan(diff)] = 0
-    assert not np.any((diff > 1e-3) & ~fragile)
+    bad = diff > 1e-3
+    print('[run_fuse {}] fused cells > 1e-3 m: {} of {} (fragile mask: {} cells)'.format(case, int(bad.sum()), bad.size,
+                                                                                       int(fragile.sum())))
+    assert not np.any(bad & ~fragile)
+    assert bad.sum() <= max(2, 1e-4 * bad.size), int(bad.sum())      # absolute cap on the escape hatch
     assert os.path.exists(os.path.join(out_dir, 'aggregate_2p5d_dsm.jpg'))
     pts, color, comments = ply2np(os.path.join(out_dir, 'aggregate_2p5d.ply'))
     assert pts.shape == (int((~np.isnan(fused)).sum()), 3) and color.shape == pts.shape

@@ -56,41 +56,50 @@ int vs_views_to_dsm(vs_ctx* ctx, int32_t n_views, const float* const* depth, con
         VS_CUDA(cudaEventRecord(ctx->fork_event, stream));
         for (int i = 0; i < NS; ++i) VS_CUDA(cudaStreamWaitEvent(ctx->side_stream[i], ctx->fork_event, 0));
     }
-    for (int v = 0; v < n_views; ++v) {
+    // On a per-view error the loop stops, but the side streams are still joined into the caller's stream below: the
+    // work already enqueued stays ordered before whatever the caller enqueues next (and a stream capture in progress
+    // stays joinable).  Planes [0, v) of dsm_stack are then complete, plane v onwards is undefined.
+    int rc = VS_OK;
+    for (int v = 0; v < n_views && rc == VS_OK; ++v) {
         const int si = dual ? v % NS : 0;
         cudaStream_t st = dual ? ctx->side_stream[si] : stream;
         uint32_t* kg = si ? ctx->d_keygrid_extra[si] : keygrid;
-        int rc = vs_keygrid_clear(ctx, kg, (int64_t)xs * ys, 4, st);
-        if (rc) return rc;
-        if (ctx->timing) VS_CUDA(cudaEventRecord(ctx->ev_pool[ctx->ev_used + 0], st));
+        rc = vs_keygrid_clear(ctx, kg, (int64_t)xs * ys, 4, st);
+        if (rc) break;
+        if (ctx->timing && cudaEventRecord(ctx->ev_pool[ctx->ev_used + 0], st) != cudaSuccess) { rc = vs_cuda_fail(cudaGetLastError(), "cudaEventRecord"); break; }
         rc = vs_unproject_rasterize(ctx, depth[v], H[v], W[v], inv_proj_mats + 16 * (size_t)v, kg, 0, nullptr,
                                     stats ? stats + (size_t)v * VS_NUM_STATS : nullptr, st);
-        if (rc) return rc;
-        if (ctx->timing) VS_CUDA(cudaEventRecord(ctx->ev_pool[ctx->ev_used + 1], st));
+        if (rc) break;
+        if (ctx->timing && cudaEventRecord(ctx->ev_pool[ctx->ev_used + 1], st) != cudaSuccess) { rc = vs_cuda_fail(cudaGetLastError(), "cudaEventRecord"); break; }
         float* plane = dsm_stack + (size_t)v * plane_stride;
         if (ctx->xch_on) {   // stage B also stores each row into the band stacks of the ranks that fuse it
             VsPeerPlan plan;
             if (!vs_peer_plan_for(ctx, plane, plane_stride, &plan)) {
                 vs_set_error("vs_views_to_dsm: dsm_stack plane is not a plane of vs_exchange.local_stack");
-                return VS_ERR_INVALID;
+                rc = VS_ERR_INVALID;
+                break;
             }
             rc = vs_grid_finalize_peer(ctx, kg, xs, ys, plane, simd_lanes, nan_counts ? nan_counts + v : nullptr, plan, st);
         } else {
             rc = vs_grid_finalize(ctx, kg, xs, ys, plane, simd_lanes, nan_counts ? nan_counts + v : nullptr, st);
         }
-        if (rc) return rc;
+        if (rc) break;
         if (ctx->timing) {
-            VS_CUDA(cudaEventRecord(ctx->ev_pool[ctx->ev_used + 2], st));
+            if (cudaEventRecord(ctx->ev_pool[ctx->ev_used + 2], st) != cudaSuccess) { rc = vs_cuda_fail(cudaGetLastError(), "cudaEventRecord"); break; }
             ctx->ev_used += 3;
         }
     }
     if (dual) {
+        const std::string first_error = rc ? std::string(vs_last_error()) : std::string();
         for (int i = 0; i < NS; ++i) {
-            VS_CUDA(cudaEventRecord(ctx->join_event[i], ctx->side_stream[i]));
-            VS_CUDA(cudaStreamWaitEvent(stream, ctx->join_event[i], 0));
+            if (cudaEventRecord(ctx->join_event[i], ctx->side_stream[i]) != cudaSuccess ||
+                cudaStreamWaitEvent(stream, ctx->join_event[i], 0) != cudaSuccess) {
+                if (rc == VS_OK) rc = vs_cuda_fail(cudaGetLastError(), "vs_views_to_dsm: join");
+            }
         }
+        if (!first_error.empty()) vs_set_error(first_error);
     }
-    return VS_OK;
+    return rc;
 }
 
 int vs_set_streams(vs_ctx* ctx, int n_streams) {

@@ -120,9 +120,10 @@ class DsmEngine:
         self.rasterize(depth, inv_proj_mat, height_map=height_map)
         return self.finalize(out=out)
 
-    def views_to_dsm(self, depths, mats, stack, first=0, count_nan=None):
+    def views_to_dsm(self, depths, mats, stack, first=0, count_nan=None, stats=None):
         """Stages A + B for a batch of views in ONE library call (vs_views_to_dsm): view i of `depths` -> stack[first + i].
-        depths: list of (H, W) float32 device tensors; mats: list of 4x4."""
+        depths: list of (H, W) float32 device tensors; mats: list of 4x4.  count_nan: optional int64 (n,) device tensor
+        (empty cells per view); stats: optional int64 (n, VS_NUM_STATS) device tensor (K1 counters per view)."""
         n = len(depths)
         if n == 0:
             return
@@ -134,7 +135,7 @@ class DsmEngine:
         assert out.is_contiguous() and out.dtype == torch.float32 and tuple(out.shape[1:]) == (self.n_size, self.e_size)
         check(lib.vs_views_to_dsm(self.ctx.handle, n, ptrs, Hs, Ws, M.ctypes.data_as(C.POINTER(C.c_double)),
                                   _ptr(self.keygrid), _ptr(out), stack.stride(0), self.simd_lanes,
-                                  _ptr(count_nan), C.c_void_p(0), _stream(self.device)), 'vs_views_to_dsm')
+                                  _ptr(count_nan), _ptr(stats), _stream(self.device)), 'vs_views_to_dsm')
 
     def capture_step(self, depths, mats, stack, fuse=True):
         """Stages A-C for a fixed set of device buffers as ONE CUDA graph (102 kernel launches + 50 memsets for 50 views): replaying
