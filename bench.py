@@ -241,11 +241,297 @@ def workload_config(cfg, n_gpus):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
-def run_b200_arm(args, cfg):
+def measure(cfg, total_views, block, world, rank, dev, steps, warmup, sparse, want_e2e, want_graph, label):
+    """Time `steps` passes of the hot path over views [block[0], block[1]) of a `total_views`-view job on this rank
+    (every rank calls this with its own block; fusion is sharded by grid-row band when world > 1).
+    Returns a dict of measurements (identical on every rank where it matters: times are the max over ranks)."""
     import torch
     import torch.distributed as dist
     from vissatsatellitestereo_b200 import engine as E, synthetic as S, distributed as D
     from vissatsatellitestereo_b200.lib import latlon_utm_converter as geo
+
+    job = S.SynthConfig(**cfg.__dict__)
+    job.n_views = total_views
+    aoi = S.make_aoi(job, geo)
+    terrain = S.Terrain(job, device=dev)
+    mats, depths = [], []
+    for v in range(block[0], block[1]):
+        M, _ = S.make_camera(job, v, aoi['alt_min'])
+        mats.append(M)
+        depths.append(S.make_depth_map(job, v, M, terrain, device=dev))
+    del terrain
+    torch.cuda.synchronize()
+    V = block[1] - block[0]
+    view_counts = [hi - lo for lo, hi in D.split_views(total_views, world)] if world > 1 else [V]
+    assert view_counts[rank if world > 1 else 0] == V
+
+    eng = E.DsmEngine(aoi, cfg.res, cfg.res, device=dev)
+    eng.collect_stats = False
+    stack = torch.empty((V, eng.n_size, eng.e_size), dtype=torch.float32, device=dev)
+    P = cfg.height * cfg.width
+    G = eng.n_size * eng.e_size
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    stage_events, exch_events, ab_events = [], [], []
+
+    xch, xch_kind = (None, 'none')
+    if world > 1 and cfg.fuse:
+        xch, xch_kind = D.make_exchange(eng, stack, view_counts, prefer=os.environ.get('VISSAT_EXCHANGE', 'peer'), sparse=sparse)
+    peer = xch_kind == 'peer-store'
+    n_waves = 5 if (world > 1 and not peer) else 1
+    wave_edges = [round(i * V / n_waves) for i in range(n_waves + 1)]
+    occ = eng.alloc_occupancy(V) if (sparse and world == 1 and cfg.fuse) else None
+    # outputs are allocated once: an allocation inside the step would put host time between the recorded events
+    rows_mine = eng.n_size if world == 1 else (lambda b: b[1] - b[0])(D.row_bands(eng.n_size, world)[rank])
+    mean_buf = torch.empty((eng.n_size, eng.e_size), dtype=torch.float32, device=dev) if world == 1 else None
+    fused_buf = torch.empty((rows_mine, eng.e_size), dtype=torch.float32, device=dev)
+
+    def step(record):
+        if record:
+            ab0, ab1 = ev(), ev()
+            ab0.record()
+        if peer:
+            xch.begin_step()
+            eng.views_to_dsm(depths, mats, stack)                        # stage B also writes the peers' row bands
+        else:
+            if occ is not None:
+                occ.zero_()
+                eng.set_occupancy(occ, stack, 0)
+            for w in range(n_waves):
+                a, b = wave_edges[w], wave_edges[w + 1]
+                eng.views_to_dsm(depths[a:b], mats[a:b], stack, first=a)     # one library call per wave (stages A + B)
+                if xch is not None:
+                    xch.send_wave(a, b)                                      # overlaps stages A/B of the next wave
+        if record:
+            ab1.record()
+            ab_events.append((ab0, ab1))
+        fe, fused = None, None
+        if cfg.fuse:
+            if record:
+                f0, f1, f2 = ev(), ev(), ev()
+                f0.record()
+            if world == 1:
+                eng.fuse(stack, out=mean_buf, occ=occ)
+                if record:
+                    f1.record()
+                fused = eng.median3x3(mean_buf, out=fused_buf, count_nan=True)
+            elif peer:
+                if record:
+                    x0 = ev()
+                    xch.finish_barrier_only()
+                    x0.record()
+                    exch_events.append((f0, x0))
+                fused, _ = xch.fuse_band(out=fused_buf, after_barrier=record)
+                if record:
+                    f1.record()
+            else:
+                if record:
+                    x0 = ev()
+                band_stack, (r0, r1), (h0, h1) = xch.finish()       # waits only for what is still in flight
+                if record:
+                    x0.record()
+                    exch_events.append((f0, x0))
+                mean = eng.fuse(band_stack)
+                if record:
+                    f1.record()
+                fused = eng.median3x3(mean, out=fused_buf, row_begin=r0, row_end=r1, in_row0=h0, h_total=eng.n_size,
+                                      count_nan=True)
+            if record:
+                f2.record()
+                fe = (f0, f1, f2)
+        if record:
+            stage_events.append(fe)
+        return fused
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # One GPU: the whole step (stages A-C) is captured once as a CUDA graph and the timed region replays it
+    # (VISSAT_GRAPH=0: eager launches).  The work is identical; the per-stage breakdown then comes from an eager
+    # instrumented pass right after the timed region.
+    graph, graph_note = None, 'eager launches'
+    if world == 1 and want_graph and os.environ.get('VISSAT_GRAPH', '1') != '0':
+        try:
+            graph = eng.capture_step(depths, mats, stack, fuse=cfg.fuse, occ=occ)
+            graph_note = 'CUDA graph replay ({} kernel launches per step captured once)'.format(graph.launches_per_replay)
+        except Exception as e:
+            graph, graph_note = None, 'eager launches (graph capture failed: {})'.format(str(e)[:120])
+            torch.cuda.synchronize()
+    for _ in range(warmup):
+        if graph is not None:
+            graph.replay()
+        else:
+            step(False)
+    barrier()
+    launches0 = eng.launch_count()
+    if graph is None:
+        eng.set_timing(True)       # CUDA events around stage A / stage B of every view, recorded inside the library
+    t0, t1 = ev(), ev()
+    barrier()
+    t0.record()
+    for _ in range(steps):
+        fused = graph.replay() if graph is not None else step(True)
+    t1.record()
+    barrier()
+    launches = graph.launches_per_replay * steps if graph is not None else eng.launch_count() - launches0
+    ms_total = t0.elapsed_time(t1)
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / steps
+    mpix_step = total_views * P / 1e6
+    value = mpix_step / (ms_step * 1e-3)
+
+    # per-stage device times: inside the timed region (eager), or from an eager instrumented pass of the same step
+    if graph is not None:
+        fused_graph = fused.clone() if fused is not None else None
+        eng.set_timing(True)
+        for _ in range(max(1, min(steps, 5))):
+            fused = step(True)
+        torch.cuda.synchronize()
+        if fused_graph is not None:
+            assert torch.equal(torch.nan_to_num(fused_graph, nan=-1e9), torch.nan_to_num(fused, nan=-1e9)), \
+                'graph replay and eager step disagree'
+    k1, k2 = eng.get_timing()
+    eng.set_timing(False)
+    # Kernel-quality numbers (roofline) come from an instrumented single-stream pass of the same step: in the timed
+    # region stage A and stage B kernels of different views overlap on 4 internal streams, which stretches every
+    # per-kernel event duration.
+    eng.set_streams(1)
+    eng.set_timing(True)
+    for _ in range(max(1, min(steps, 3))):
+        step(False)
+    torch.cuda.synchronize()
+    k1_iso, k2_iso = eng.get_timing()
+    eng.set_timing(False)
+    eng.set_streams(4)
+    fuse_ms = np.array([fe[0].elapsed_time(fe[1]) for fe in stage_events if fe]) if cfg.fuse else np.array([0.0])
+    blur_ms = np.array([fe[1].elapsed_time(fe[2]) for fe in stage_events if fe]) if cfg.fuse else np.array([0.0])
+    exch_ms = np.array([a.elapsed_time(b) for a, b in exch_events]) if exch_events else np.array([0.0])
+    ab_ms = np.array([a.elapsed_time(b) for a, b in ab_events])          # stages A+B of all V views, per step
+    inst_total = float(ab_ms.sum() + fuse_ms.sum() + blur_ms.sum())
+    occupancy_frac = None
+    nvlink = None
+    if occ is not None:
+        occupancy_frac = float(_bitmap_fraction(occ, V))
+    if peer and xch.sparse:
+        xch.keep_last_occ = True            # one more step, keeping a copy of the bitmap the fusion consumed
+        step(False)
+        torch.cuda.synchronize()
+        xch.keep_last_occ = False
+        last = getattr(xch, '_last_occ', None)
+        if last is not None:
+            recv = _received_bytes(xch, last, rank, world, view_counts)
+            t = torch.tensor([recv], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dense = total_views * 4.0 * G * (world - 1) / world ** 2
+            t_ab = float(ab_ms.mean()) * 1e-3
+            nvlink = {'bytes_per_gpu_per_dir_sparse_max': float(t.item()), 'bytes_per_gpu_per_dir_dense': dense,
+                      'sparse_over_dense': float(t.item()) / dense if dense else None,
+                      'gbs_during_stages_ab': float(t.item()) / t_ab / 1e9 if t_ab > 0 else None,
+                      'frac_of_770_gbs': float(t.item()) / t_ab / 1e9 / 770.0 if t_ab > 0 else None,
+                      'note': 'the exchange is written by the stage-B kernels (peer stores over NVLink), so it is spread over '
+                              'stages A+B; bytes are counted from the owners\' occupancy bitmaps (marked tiles of remote views)'}
+    stages = {'k1_unproject_scatter_ms_per_view': float(k1.mean()), 'k2_grid_finalize_ms_per_view': float(k2.mean()),
+              'k1_isolated_ms_per_view': float(k1_iso.mean()), 'k2_isolated_ms_per_view': float(k2_iso.mean()),
+              'k3_fuse_ms_per_step' if world == 1 else 'exchange_plus_fuse_ms_per_step': float(fuse_ms.mean()),
+              'exchange_ms_per_step': float(exch_ms.mean()),
+              'stages_ab_ms_per_step': float(ab_ms.mean()), 'stages_ab_effective_ms_per_view': float(ab_ms.mean() / max(V, 1)),
+              'note': 'stage A of view v+1 overlaps stage B of view v on internal streams, so the per-kernel '
+                      'durations k1/k2 are measured under concurrency and add up to more than stages_ab',
+              'k4_median3x3_ms_per_step': float(blur_ms.mean()),
+              'launch': graph_note, 'sparse': bool(sparse), 'tile_occupancy': occupancy_frac,
+              'share_of_step': {'k1': float(k1.sum() / inst_total), 'k2': float(k2.sum() / inst_total),
+                                'fuse': float(fuse_ms.sum() / inst_total), 'blur': float(blur_ms.sum() / inst_total)}}
+
+    res = {'label': label, 'value': value, 'ms_per_step': ms_step, 'launches': int(launches), 'stages': stages,
+           'V': V, 'P': P, 'G': G, 'k1_iso': float(k1_iso.mean()), 'k2_iso': float(k2_iso.mean()),
+           'k1': float(k1.mean()), 'k2': float(k2.mean()), 'fuse_ms': float(fuse_ms.mean()), 'blur_ms': float(blur_ms.mean()),
+           'ab_ms': float(ab_ms.mean()), 'graph_note': graph_note, 'xch_kind': xch_kind, 'fit': eng.fit, 'nvlink': nvlink,
+           'mpix_step': mpix_step, 'rows_mine': rows_mine, 'e2e': None}
+
+    # ---- e2e: pinned host depth maps -> H2D -> kernels -> D2H of per-view DSMs + fused DSM, every step
+    if want_e2e:
+        host_depths = [d.cpu().pin_memory() for d in depths]
+        host_views = torch.empty((V, eng.n_size, eng.e_size), dtype=torch.float32).pin_memory()
+        host_fused = torch.empty((rows_mine, eng.e_size), dtype=torch.float32).pin_memory()
+
+        def e2e_step():
+            if world == 1:
+                eng.process_host(host_depths, mats, host_views, host_fused, stack=stack, fuse=cfg.fuse)
+                return
+            # every rank: its views host -> device -> per-view DSMs -> host; then exchange, fuse own band, band -> host
+            eng.process_host(host_depths, mats, host_views, None, stack=stack, fuse=False)
+            if cfg.fuse:
+                band, _ = D.fuse_distributed(eng, stack, view_counts)
+                host_fused.copy_(band, non_blocking=True)
+                torch.cuda.synchronize()
+
+        eng.set_occupancy(None)
+        for _ in range(max(1, min(warmup, 2))):
+            e2e_step()
+        n_e2e = max(1, min(steps, 5))
+        barrier()
+        w0 = time.perf_counter()
+        e0, e1 = ev(), ev()
+        e0.record()
+        for _ in range(n_e2e):
+            e2e_step()
+        e1.record()
+        barrier()
+        wall = (time.perf_counter() - w0) / n_e2e
+        dev_ms = e0.elapsed_time(e1) / n_e2e
+        t_e2e = max(wall, dev_ms * 1e-3)
+        if world > 1:
+            t = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_e2e = float(t.item())
+        res['e2e'] = {'value': mpix_step / t_e2e, 'unit': UNIT, 'h2d_bytes_per_step': int(V * P * 4) * world,
+                      'd2h_bytes_per_step': int(V * G * 4) * world + (G * 4 if cfg.fuse else 0), 'ms_per_step': 1e3 * t_e2e,
+                      'steps': n_e2e, 'api': 'DsmEngine.process_host (pinned host buffers in/out, 3 streams)' +
+                      ('' if world == 1 else ' per rank + NCCL row-band exchange + per-rank fused band to host')}
+        if cfg.fuse and world == 1 and fused is not None:
+            assert np.array_equal(host_fused.numpy(), fused.cpu().numpy(), equal_nan=True), 'e2e result differs'
+    if peer:
+        xch.close()
+    eng.close()
+    del stack, depths
+    torch.cuda.empty_cache()
+    return res
+
+
+def _bitmap_fraction(occ, V):
+    import torch
+    g = torch.arange(V, device=occ.device)
+    bits = (occ[:, :, g // 32] >> (g % 32).to(torch.int32)) & 1
+    return bits.float().mean().item()
+
+
+def _received_bytes(xch, occ, rank, world, view_counts):
+    """Bytes this rank's band stack received from OTHER ranks in one step, from its occupancy bitmap: for every marked
+    (tile, view) with a remote view, the rows of the tile inside this rank's band (+ halo) x 64 columns x 4 bytes."""
+    import torch
+    from vissatsatellitestereo_b200 import _native
+    Ty, Tx, _ = occ.shape
+    V = sum(view_counts)
+    first = sum(view_counts[:rank])
+    g = torch.arange(V, device=occ.device)
+    remote = (g < first) | (g >= first + view_counts[rank])
+    bits = ((occ[:, :, g // 32] >> (g % 32).to(torch.int32)) & 1).bool() & remote[None, None, :]
+    ty = torch.arange(Ty, device=occ.device)
+    rows = (torch.clamp((ty + 1) * _native.VS_TILE_H, max=xch.h1) - torch.clamp(ty * _native.VS_TILE_H, min=xch.h0)).clamp(min=0)
+    tx = torch.arange(Tx, device=occ.device)
+    cols = (torch.clamp((tx + 1) * _native.VS_TILE_W, max=xch.W) - tx * _native.VS_TILE_W).clamp(min=0)
+    cells = rows[:, None] * cols[None, :]
+    return float((bits.sum(dim=2) * cells).sum().item()) * 4.0
+
+
+def run_b200_arm(args, cfg):
+    import torch
+    import torch.distributed as dist
+    from vissatsatellitestereo_b200 import engine as E, synthetic as S, distributed as D
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -262,251 +548,75 @@ def run_b200_arm(args, cfg):
         dist.init_process_group('nccl', device_id=dev)
     assert world == args.gpus, 'launch with torchrun --nproc-per-node {} (WORLD_SIZE={})'.format(args.gpus, world)
 
-    # ---- synthetic inputs, generated on the device (untimed).  Rank r holds views [r*V, (r+1)*V) of the job.
+    # ---- headline: weak scaling, rank r holds views [r*V, (r+1)*V) of a (V * world)-view job over the same grid
     V = cfg.n_views
-    job = S.SynthConfig(**cfg.__dict__)
-    job.n_views = V * world
-    aoi = S.make_aoi(job, geo)
-    terrain = S.Terrain(job, device=dev)
-    mats, depths = [], []
-    for v in range(rank * V, (rank + 1) * V):
-        M, _ = S.make_camera(job, v, aoi['alt_min'])
-        mats.append(M)
-        depths.append(S.make_depth_map(job, v, M, terrain, device=dev))
-    del terrain
-    torch.cuda.synchronize()
-
-    eng = E.DsmEngine(aoi, cfg.res, cfg.res, device=dev)
-    eng.collect_stats = False
-    stack = torch.empty((V, eng.n_size, eng.e_size), dtype=torch.float32, device=dev)
-    view_counts = [V] * world
-    P = cfg.height * cfg.width
-    G = eng.n_size * eng.e_size
-
-    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
-    stage_events = []
-    exch_events = []
-    ab_events = []
-
-    n_waves = 5 if world > 1 else 1
-    wave_edges = [round(i * V / n_waves) for i in range(n_waves + 1)]
-
-    # multi-GPU transpose (views -> row bands): stage B stores the bands into the peers' stacks itself (CUDA-IPC peer
-    # memory over NVLink); VISSAT_EXCHANGE=nccl selects the NCCL send/recv waves instead.  Buffers are allocated once.
-    xch, xch_kind = (D.make_exchange(eng, stack, view_counts, prefer=os.environ.get('VISSAT_EXCHANGE', 'peer'))
-                     if (world > 1 and cfg.fuse) else (None, 'none'))
-    peer = xch_kind == 'peer-store'
-
-    def step(record):
-        if record:
-            ab0, ab1 = ev(), ev()
-            ab0.record()
-        if peer:
-            xch.begin_step()
-            eng.views_to_dsm(depths, mats, stack)                        # stage B also writes the peers' row bands
-        else:
-            for w in range(n_waves):
-                a, b = wave_edges[w], wave_edges[w + 1]
-                eng.views_to_dsm(depths[a:b], mats[a:b], stack, first=a)     # one library call per wave (stages A + B)
-                if xch is not None:
-                    xch.send_wave(a, b)                                      # overlaps stages A/B of the next wave
-        if record:
-            ab1.record()
-            ab_events.append((ab0, ab1))
-        fe = None
-        if cfg.fuse:
-            if record:
-                f0, f1, f2 = ev(), ev(), ev()
-                f0.record()
-            if world == 1:
-                mean = eng.fuse(stack)
-                if record:
-                    f1.record()
-                fused = eng.median3x3(mean, count_nan=True)
-            else:
-                if record:
-                    x0 = ev()
-                band_stack, (r0, r1), (h0, h1) = xch.finish()       # waits only for what is still in flight
-                if record:
-                    x0.record()
-                mean = eng.fuse(band_stack)
-                if record:
-                    f1.record()
-                fused = eng.median3x3(mean, row_begin=r0, row_end=r1, in_row0=h0, h_total=eng.n_size, count_nan=True)
-                if record:
-                    exch_events.append((f0, x0))
-            if record:
-                f2.record()
-                fe = (f0, f1, f2)
-        else:
-            fused = None
-        if record:
-            stage_events.append(fe)
-        return fused
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # One GPU: the whole step (stages A-C, 3 launches per view + fusion + blur) is captured once as a CUDA graph and
-    # the timed region replays it (VISSAT_GRAPH=0: eager launches).  The work is identical; the per-stage breakdown
-    # then comes from an eager instrumented pass right after the timed region.
-    graph, graph_note = None, 'eager launches'
-    if world == 1 and os.environ.get('VISSAT_GRAPH', '1') != '0':
-        try:
-            graph = eng.capture_step(depths, mats, stack, fuse=cfg.fuse)
-            graph_note = 'CUDA graph replay ({} kernel launches per step captured once)'.format(graph.launches_per_replay)
-        except Exception as e:
-            graph, graph_note = None, 'eager launches (graph capture failed: {})'.format(str(e)[:120])
-            torch.cuda.synchronize()
-    for _ in range(args.warmup):
-        if graph is not None:
-            graph.replay()
-        else:
-            step(False)
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    launches0 = eng.launch_count()
-    if graph is None:
-        eng.set_timing(True)       # CUDA events around stage A / stage B of every view, recorded inside the library
-    t0, t1 = ev(), ev()
-    barrier()
-    t0.record()
-    for _ in range(args.steps):
-        fused = graph.replay() if graph is not None else step(True)
-    t1.record()
-    barrier()
-    launches = graph.launches_per_replay * args.steps if graph is not None else eng.launch_count() - launches0
-    ms_total = t0.elapsed_time(t1)
-    if world > 1:
-        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-    ms_step = ms_total / args.steps
-    mpix_step = V * world * P / 1e6
-    value = mpix_step / (ms_step * 1e-3)
-
-    # per-stage device times: inside the timed region (eager), or from an eager instrumented pass of the same step
-    if graph is not None:
-        fused_graph = fused.clone() if fused is not None else None
-        eng.set_timing(True)
-        for _ in range(max(1, min(args.steps, 5))):
-            fused = step(True)
-        torch.cuda.synchronize()
-        if fused_graph is not None:
-            assert torch.equal(torch.nan_to_num(fused_graph, nan=-1e9), torch.nan_to_num(fused, nan=-1e9)), \
-                'graph replay and eager step disagree'
-    k1, k2 = eng.get_timing()
-    eng.set_timing(False)
-    # The timed region overlaps stage A and stage B kernels of different views on 4 internal streams, which
-    # stretches every per-kernel event duration.  Kernel-quality numbers (roofline) therefore also come from an
-    # instrumented single-stream pass of the same step, run right after the timed region.
-    eng.set_streams(1)
-    eng.set_timing(True)
-    for _ in range(max(1, min(args.steps, 3))):
-        step(False)
-    torch.cuda.synchronize()
-    k1_iso, k2_iso = eng.get_timing()
-    eng.set_timing(False)
-    eng.set_streams(4)
-    fuse_ms = np.array([fe[0].elapsed_time(fe[1]) for fe in stage_events if fe]) if cfg.fuse else np.array([0.0])
-    blur_ms = np.array([fe[1].elapsed_time(fe[2]) for fe in stage_events if fe]) if cfg.fuse else np.array([0.0])
-    exch_ms = np.array([a.elapsed_time(b) for a, b in exch_events]) if exch_events else np.array([0.0])
-    ab_ms = np.array([a.elapsed_time(b) for a, b in ab_events])          # stages A+B of all V views, per step
-    inst_total = float(ab_ms.sum() + fuse_ms.sum() + blur_ms.sum())      # instrumented (eager) time the shares refer to
-    stages = {'k1_unproject_scatter_ms_per_view': float(k1.mean()), 'k2_grid_finalize_ms_per_view': float(k2.mean()),
-              'k1_isolated_ms_per_view': float(k1_iso.mean()), 'k2_isolated_ms_per_view': float(k2_iso.mean()),
-              'k3_fuse_ms_per_step' if world == 1 else 'exchange_plus_fuse_ms_per_step': float(fuse_ms.mean()),
-              'exchange_ms_per_step': float(exch_ms.mean()),
-              'stages_ab_ms_per_step': float(ab_ms.mean()), 'stages_ab_effective_ms_per_view': float(ab_ms.mean() / V),
-              'note': 'stage A of view v+1 overlaps stage B of view v on two internal streams, so the per-kernel '
-                      'durations k1/k2 are measured under concurrency and add up to more than stages_ab',
-              'k4_median3x3_ms_per_step': float(blur_ms.mean()),
-              'launch': graph_note,
-              'share_of_step': {'k1': float(k1.sum() / inst_total), 'k2': float(k2.sum() / inst_total),
-                                'fuse': float(fuse_ms.sum() / inst_total), 'blur': float(blur_ms.sum() / inst_total)}}
-
-    # ---- e2e: pinned host depth maps -> H2D -> kernels -> D2H of per-view DSMs + fused DSM, every step
-    e2e = None
+    head = measure(cfg, V * world, (rank * V, (rank + 1) * V), world, rank, dev, args.steps, args.warmup,
+                   sparse=cfg.random_offsets, want_e2e=True, want_graph=True, label=cfg.name)
     clocks = sampler.stop() if rank == 0 else None
-    if True:
-        host_depths = [d.cpu().pin_memory() for d in depths]
-        host_views = torch.empty((V, eng.n_size, eng.e_size), dtype=torch.float32).pin_memory()
-        rows_mine = eng.n_size if world == 1 else (lambda b: b[1] - b[0])(D.row_bands(eng.n_size, world)[rank])
-        host_fused = torch.empty((rows_mine, eng.e_size), dtype=torch.float32).pin_memory()
 
-        def e2e_step():
-            if world == 1:
-                eng.process_host(host_depths, mats, host_views, host_fused, stack=stack, fuse=cfg.fuse)
-                return
-            # every rank: its views host -> device -> per-view DSMs -> host; then exchange, fuse own band, band -> host
-            eng.process_host(host_depths, mats, host_views, None, stack=stack, fuse=False)
-            if cfg.fuse:
-                band, _ = D.fuse_distributed(eng, stack, view_counts)
-                host_fused.copy_(band, non_blocking=True)
-                torch.cuda.synchronize()
+    # ---- second record: BASELINE.json configs[2] (C3, the config north_star names for the all-to-all), STRONG scaling:
+    # its 200 views are split over the ranks, fusion by row band with the sparse exchange.  Few steps (a step is ~0.1 s).
+    c3 = None
+    if not args.no_c3 and cfg.name == 'C2':
+        c3cfg = S.SynthConfig(**S.CONFIGS['C3'].__dict__)
+        blk = D.split_views(c3cfg.n_views, world)[rank]
+        r3 = measure(c3cfg, c3cfg.n_views, blk, world, rank, dev, steps=3, warmup=1, sparse=True, want_e2e=False,
+                     want_graph=True, label='C3')
+        peak3, _ = load_peaks()
+        b_alg3 = c3cfg.n_views * 4.0 * r3['P'] + 2 * c3cfg.n_views * 4.0 * r3['G'] + 4.0 * r3['G']
+        c3 = {'workload': 'C3 (BASELINE.json configs[2]): 200 views x 4096x4096 depth -> 8192x8192 grid @ 0.3 m, the 200 views '
+                          'split over {} GPU(s), fusion by grid-row band'.format(world),
+              'scaling': 'strong', 'n_gpus': world, 'value': r3['value'], 'unit': UNIT, 'ms_per_step': r3['ms_per_step'],
+              'steps': 3, 'warmup': 1, 'algorithmic_bytes_per_step': b_alg3,
+              'achieved_gbs': b_alg3 / (r3['ms_per_step'] * 1e-3) / 1e9,
+              'frac_of_hbm_peak': b_alg3 / (r3['ms_per_step'] * 1e-3) / 1e9 / (peak3 * world),
+              'stages': r3['stages'], 'exchange': r3['xch_kind'], 'nvlink': r3['nvlink'], 'fit': r3['fit'],
+              'gpu_launches': r3['launches']}
 
-        for _ in range(max(1, min(args.warmup, 2))):
-            e2e_step()
-        n_e2e = max(1, min(args.steps, 5))
-        barrier()
-        w0 = time.perf_counter()
-        e0, e1 = ev(), ev()
-        e0.record()
-        for _ in range(n_e2e):
-            e2e_step()
-        e1.record()
-        barrier()
-        wall = (time.perf_counter() - w0) / n_e2e
-        dev_ms = e0.elapsed_time(e1) / n_e2e
-        t_e2e = max(wall, dev_ms * 1e-3)
-        if world > 1:
-            t = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            t_e2e = float(t.item())
-        e2e = {'value': mpix_step / t_e2e, 'unit': UNIT, 'h2d_bytes_per_step': int(V * P * 4) * world,
-               'd2h_bytes_per_step': int(V * G * 4) * world + (G * 4 if cfg.fuse else 0), 'ms_per_step': 1e3 * t_e2e,
-               'steps': n_e2e, 'host_numa_node': numa_node, 'api': 'DsmEngine.process_host (pinned host buffers in/out, 3 streams)' +
-               ('' if world == 1 else ' per rank + NCCL row-band exchange + per-rank fused band to host')}
-        if cfg.fuse and world == 1:
-            assert np.array_equal(host_fused.numpy(), fused.cpu().numpy(), equal_nan=True), 'e2e result differs'
+    # ---- N > 1: the N-rank result must equal the single-rank result bit for bit (both transports, small grids)
+    mgpu = None
+    if world > 1:
+        from vissatsatellitestereo_b200 import mgpu_selfcheck
+        mgpu = mgpu_selfcheck.run(dev, rank, world)
 
-    if peer:
-        xch.close()
     if affinity0 is not None:
         os.sched_setaffinity(0, affinity0)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
+        if mgpu is not None and not mgpu['bit_identical']:
+            sys.exit(3)
         return
 
     peak, peak_src = load_peaks()
+    P, G = head['P'], head['G']
     # dominant kernel and its roofline (algorithmic bytes per launch / measured launch duration)
-    per_step = {'k1': k1_iso.mean() * V, 'k2': k2_iso.mean() * V, 'fuse': fuse_ms.mean(), 'blur': blur_ms.mean()}
-    alg = {'k1': (4.0 * P, k1_iso.mean(), 'k_unproject_scatter: 4 B/pixel depth read'),
-           'k2': (8.0 * G, k2_iso.mean(), 'k_grid_finalize: 4 B/cell key read + 4 B/cell DSM write'),
-           'fuse': (4.0 * G * V * world / world + 4.0 * G / world, fuse_ms.mean(),
-                    'k_fuse: 4 B/cell/view read + 4 B/cell write'),
-           'blur': (8.0 * G / world, blur_ms.mean(), 'k_median3x3: 4 B read + 4 B write per cell')}
+    per_step = {'k1': head['k1_iso'] * V, 'k2': head['k2_iso'] * V, 'fuse': head['fuse_ms'], 'blur': head['blur_ms']}
+    alg = {'k1': (4.0 * P, head['k1_iso'], 'k_unproject_scatter: 4 B/pixel depth read'),
+           'k2': (8.0 * G, head['k2_iso'], 'k_grid_finalize: 4 B/cell key read + 4 B/cell DSM write'),
+           'fuse': (4.0 * G * V + 4.0 * G / world, head['fuse_ms'], 'k_fuse: 4 B/cell/view read + 4 B/cell write'),
+           'blur': (8.0 * G / world, head['blur_ms'], 'k_median3x3: 4 B read + 4 B write per cell')}
     top = max(per_step, key=per_step.get)
     if world > 1 and top in ('fuse', 'blur'):
         top = 'k1' if per_step['k1'] >= per_step['k2'] else 'k2'      # exchange time is not a kernel roofline
     bytes_launch, ms_launch, what = alg[top]
     achieved = bytes_launch / (ms_launch * 1e-3) / 1e9
-    pair_bytes = 4.0 * P + 8.0 * G
-    pair_gbs = pair_bytes / (ab_ms.mean() / V * 1e-3) / 1e9
+    # stages A+B of one view with SURVEY 8(d) bytes: depth read + per-view DSM write (key-grid traffic is overhead)
+    pair_bytes = 4.0 * P + 4.0 * G
+    pair_gbs = pair_bytes / (head['ab_ms'] / V * 1e-3) / 1e9
     roofline = {'bound': 'hbm', 'kernel': what, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                'stages_ab_pair': {'algorithmic_bytes_per_view': pair_bytes, 'effective_ms_per_view': float(ab_ms.mean() / V),
+                'stages_ab_pair': {'algorithmic_bytes_per_view': pair_bytes, 'effective_ms_per_view': head['ab_ms'] / V,
                                    'achieved': pair_gbs, 'frac': pair_gbs / peak,
-                                   'what': 'K1 + K2 of one view (4 B/pixel + 8 B/cell) over the effective per-view time '
-                                           'of the overlapped pipeline'},
+                                   'what': 'K1 + K2 of one view with SURVEY 8(d) bytes (4 B/pixel depth read + 4 B/cell per-view '
+                                           'DSM write; the key grid between them is overhead, not credit) over the effective '
+                                           'per-view time of the overlapped pipeline'},
                 'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
                 'algorithmic_bytes_per_launch': bytes_launch, 'avg_launch_ms': float(ms_launch),
-                'avg_launch_ms_in_timed_region': float({'k1': k1.mean(), 'k2': k2.mean(), 'fuse': fuse_ms.mean(),
-                                                        'blur': blur_ms.mean()}[top]),
+                'avg_launch_ms_in_timed_region': float({'k1': head['k1'], 'k2': head['k2'], 'fuse': head['fuse_ms'],
+                                                        'blur': head['blur_ms']}[top]),
                 'timing': 'CUDA events recorded inside the library around every launch; avg_launch_ms is from an '
                           'instrumented single-stream pass right after the timed region (in the timed region stage A '
                           'and stage B kernels of different views run concurrently on 4 streams, which stretches '
@@ -516,12 +626,16 @@ def run_b200_arm(args, cfg):
     if os.path.exists(traffic_file):
         try:
             with open(traffic_file) as fp:
-                roofline['traffic'] = json.load(fp).get(top)
+                tj = json.load(fp)
+            roofline['traffic'] = tj.get(top)
+            roofline['traffic_source'] = tj.get('_source', 'profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum '
+                                                'per launch from a committed `ncu --set full` capture (not measured in this run)')
         except Exception:
             pass
-    # whole-pipeline algorithmic bytes (SURVEY.md §8d B_alg) for context
-    b_alg = V * world * 4.0 * P + V * world * 4.0 * G + (V * world * 4.0 * G + 4.0 * G if cfg.fuse else 0.0)
-    pipeline_gbs = b_alg / (ms_step * 1e-3) / 1e9
+    # whole-pipeline algorithmic bytes (SURVEY.md 8d B_alg) for context
+    Vt = V * world
+    b_alg = Vt * 4.0 * P + Vt * 4.0 * G + (Vt * 4.0 * G + 4.0 * G if cfg.fuse else 0.0)
+    pipeline_gbs = b_alg / (head['ms_per_step'] * 1e-3) / 1e9
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -531,23 +645,30 @@ def run_b200_arm(args, cfg):
         cpu = {'value': r['value'], 'unit': UNIT, 'cores': min(cores, cfg.n_views), 'kind': 'port',
                'sample': r['sample'], 'host_cpu_count': cores}
 
-    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
-            'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak',
+    e2e = head['e2e']
+    if e2e is not None:
+        e2e['host_numa_node'] = numa_node
+    line = {'metric': METRIC, 'value': head['value'], 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': head['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': workload_config(cfg, world),
-            'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline,
-            'cpu_baseline': cpu, 'stages': stages,
+            'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(head['launches']), 'roofline': roofline,
+            'cpu_baseline': cpu, 'stages': head['stages'],
             'pipeline': {'algorithmic_bytes_per_step': b_alg, 'achieved_gbs': pipeline_gbs,
                          'frac_of_hbm_peak': pipeline_gbs / (peak * world)},
-            'fit': eng.fit}
-    line['config']['launch'] = graph_note
+            'fit': head['fit'], 'c3': c3}
+    line['config']['launch'] = head['graph_note']
     if world > 1:
         line['config']['exchange'] = {'peer-store': 'stage-B kernel stores row bands into the peers\' stacks '
                                                     '(CUDA IPC peer memory over NVLink) + 1-element all-reduce barrier',
                                       'nccl-waves': 'NCCL grouped send/recv in 5 waves overlapped with stages A/B',
-                                      'none': 'none (no fusion)'}[xch_kind]
+                                      'none': 'none (no fusion)'}[head['xch_kind']]
+        line['mgpu_bit_identical'] = bool(mgpu['bit_identical'])
+        line['mgpu_check'] = mgpu
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+        if not mgpu['bit_identical']:
+            sys.exit(3)
 
 
 def main():
@@ -559,6 +680,7 @@ def main():
     ap.add_argument('--config', default='C2')
     ap.add_argument('--views', type=int, default=None, help='override views per GPU (debugging)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-c3', action='store_true', help='skip the C3 (strong-scaling, sparse exchange) sub-record')
     args = ap.parse_args()
     from vissatsatellitestereo_b200 import synthetic as S
     cfg = S.SynthConfig(**S.CONFIGS[args.config].__dict__)

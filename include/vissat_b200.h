@@ -31,7 +31,7 @@ extern "C" {
 #define VS_ERR_STATE 3   /* call order (e.g. rasterize before vs_set_aoi) */
 #define VS_ERR_FIT 4     /* AOI polynomial could not be validated; exact mode is still available */
 
-#define VS_ABI_VERSION 1
+#define VS_ABI_VERSION 2
 
 typedef struct vs_ctx vs_ctx;
 
@@ -193,14 +193,32 @@ typedef struct vs_exchange {
     int32_t n_ranks;
     int32_t rank;
     int32_t halo;              /* rows of neighbouring bands kept on each side (1 for the 3x3 blur) */
-    int32_t reserved;
+    int32_t occ_words;         /* words per tile of the occupancy bitmaps below (>= ceil(n_views_total / 32)); 0 = none */
     int64_t view0;             /* global index of this rank's first view */
     int64_t n_views_total;
     const float* local_stack;  /* base of the local per-view DSM stack (plane 0) */
     float* band_stack[VS_MAX_RANKS];
+    /* Sparse exchange (SURVEY.md 8(e) "skip all-NaN row-bands via an occupancy flag"), used when occ_words > 0:
+     * occ[j] is rank j's occupancy bitmap (layout: see vs_set_occupancy), peer-mapped like band_stack[j].  Stage B
+     * then sets the bit of (tile, view) in the bitmap of every rank whose band (+ halo) the tile touches, and does
+     * NOT store all-empty tiles into the band stacks: the owner's vs_fuse_views_sparse never reads an unmarked tile. */
+    uint32_t* occ[VS_MAX_RANKS];
 } vs_exchange;
 /* Enable (ex != NULL; the struct is copied) or disable (ex == NULL) the peer stores of vs_views_to_dsm. */
 int vs_set_exchange(vs_ctx* ctx, const vs_exchange* ex);
+
+/* ---- occupancy bitmap: which (tile, view) pairs hold data ----------------------------------------------------------
+ * On large AOIs a view covers a fraction of the grid (BASELINE.json configs[2]: ~1/3), so most (tile, view) pairs of
+ * the per-view DSM stack are all-NaN.  Stage B knows which: it already skips the arithmetic of tiles whose key box is
+ * empty.  With a bitmap set, it records the others: occ is uint32 [ceil(ysize / VS_TILE_H)][ceil(xsize / VS_TILE_W)]
+ * [occ_words]; bit (g % 32) of word (g / 32) of tile (ty, tx) is set when global view g may hold a non-NaN value in
+ * grid rows [32 ty, 32 ty + 32) x columns [64 tx, 64 tx + 64).  The caller zeroes the bitmap before a pass over the
+ * views; vs_fuse_views_sparse reads, per tile, only the marked planes.
+ * Plane `dsm_stack + i * plane_stride` of vs_views_to_dsm is global view view0 + (that plane - stack_base) / plane_stride.
+ * occ == NULL switches the marking off. */
+#define VS_TILE_W 64
+#define VS_TILE_H 32
+int vs_set_occupancy(vs_ctx* ctx, uint32_t* occ, int32_t occ_words, const float* stack_base, int64_t view0);
 
 /* ---- stage C: cross-view fusion --------------------------------------------------------------------------
  * Replaces aggregate_2p5d.py:65-78: per cell over V views (in the given order = sorted file order):
@@ -213,6 +231,14 @@ int vs_set_exchange(vs_ctx* ctx, const vs_exchange* ex);
  */
 int vs_fuse_views(vs_ctx* ctx, const float* views, int64_t plane_stride, int32_t n_views, int32_t rows, int32_t W,
                   float* out_mean, void* stream);
+
+/* The same fusion, reading only the planes the occupancy bitmap marks (an unmarked (tile, view) pair counts as NaN and
+ * its memory is never touched).  `views` planes hold grid rows [row0, row0 + rows) of an xsize = W wide grid whose
+ * bitmap `occ` (full-grid tile indexing as above, n_tile_cols = ceil(W / VS_TILE_W)) was filled by stage B.  The result
+ * is bit-identical to vs_fuse_views on the densified stack: numpy's summation order depends on the original view
+ * indices, which are kept. */
+int vs_fuse_views_sparse(vs_ctx* ctx, const float* views, int64_t plane_stride, int32_t n_views, int32_t rows, int32_t W,
+                         int32_t row0, const uint32_t* occ, int32_t occ_words, float* out_mean, void* stream);
 
 /* aggregate_2p5d.py:81 (and the blur half of produce_dsm.py:58): cv2.medianBlur(float32, 3) on rows
  * [row_begin, row_end) of an image of H_total rows.  `in` points at image row `in_row0`; rows

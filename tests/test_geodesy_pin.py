@@ -210,7 +210,7 @@ def test_k1_polynomial_vs_exact(mp_golden, name):
     c, h = np.array(eng.fit['box_center']), np.array(eng.fit['box_half'])
     pts = a_in[m, :3]
     inside = np.all(np.abs((pts - c) / h) <= 1.0, axis=1)
-    assert inside.sum() >= 1000, inside.sum()
+    assert inside.sum() >= 300, inside.sum()
     colf, rowf, alt = eng.eval_poly(pts[inside])
     g = a_out[m][inside]
     E = g[:, 6] + g[:, 7]

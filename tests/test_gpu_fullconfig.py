@@ -27,7 +27,8 @@ from oracle import geodesy, pipeline as op
 pytestmark = pytest.mark.gpu
 
 HEIGHT_TOL = 1e-3          # metres (north_star)
-BAD_CELL_CAP = 1e-4        # fraction of compared fused cells that may exceed HEIGHT_TOL (all must be fragile)
+BAD_CELL_CAP = 2e-4        # fraction of compared fused cells that may exceed HEIGHT_TOL (all must be fragile);
+                           # measured: C1 0, C2 1.5e-5, C3 7.5e-5, C5 9.5e-5 (a 1-ulp per-view difference flipping the strict MAD test)
 N_THREADS = max(1, min(16, os.cpu_count() or 1))
 
 
@@ -63,13 +64,15 @@ def _oracle_bands(depths, mats, aoi, cfg, bands, skip_far_views=False):
             rng = op.view_row_range(d, mats[v], aoi, cfg.res)
             todo = [] if rng is None else [b for b in todo if bands[b][1] + 2 > rng[0] and bands[b][0] - 2 < rng[1]]
         outs = [np.full((re - rb, e_size), np.nan, dtype=np.float32) for rb, re in bands]
-        info = {'ambiguous': [0] * len(bands), 'ambiguous_cells': [np.zeros((0, 2), np.int64)] * len(bands)}
+        info = {'ambiguous': [0] * len(bands), 'ambiguous_cells': [np.zeros((0, 2), np.int64)] * len(bands),
+                'n_in_window': [0] * len(bands)}
         if todo:
             got, inf = op.convert_depth_map_rows(d, mats[v], aoi, cfg.res, cfg.res, [bands[b] for b in todo])
             for k, b in enumerate(todo):
                 outs[b] = got[k]
                 info['ambiguous'][b] = inf['ambiguous'][k]
                 info['ambiguous_cells'][b] = inf['ambiguous_cells'][k]
+                info['n_in_window'][b] = inf['n_in_window'][k]
         return outs, info
 
     with ThreadPoolExecutor(N_THREADS) as pool:
@@ -169,7 +172,10 @@ def _run_config(name, bands, lanes, views=None, per_view_only=False, check_views
               '{} cells), max |diff| elsewhere {:.2e} m'.format(name, rep['cells'], rep['bit_identical'] / rep['cells'],
                                                                rep['bad'], HEIGHT_TOL, rep['fragile'], rep['max_diff_ok']))
         assert rep['bad'] <= max(2, BAD_CELL_CAP * rep['cells']), rep
-    assert n_amb <= 4, 'unexpectedly many points within 1e-7 cell of an edge: {}'.format(n_amb)
+    # a point lies within 1e-7 cell of one of its 4 cell edges with probability 4e-7: the count must be of that order
+    n_pts = sum(sum(i['n_in_window']) for i in infos)
+    assert n_amb <= 8 + 5 * 4e-7 * n_pts, 'unexpectedly many points within 1e-7 cell of an edge: {} of {}'.format(n_amb, n_pts)
+    assert int(st[:, 2].sum()) <= 8 + 5 * 4e-7 * int(st[:, 1].sum())
     eng.close()
     return pv, rep
 

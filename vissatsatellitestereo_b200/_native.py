@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, 'libvissat_b200.so')
 
 VS_NUM_STATS = 4
 STAT_VALID, STAT_INGRID, STAT_AMBIGUOUS, STAT_EXACT = 0, 1, 2, 3
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class VisSatError(RuntimeError):
@@ -38,10 +38,14 @@ VS_MAX_RANKS = 16
 VS_IPC_HANDLE_BYTES = 64
 
 
+VS_TILE_W = 64
+VS_TILE_H = 32
+
+
 class vs_exchange(C.Structure):
-    _fields_ = [('n_ranks', C.c_int32), ('rank', C.c_int32), ('halo', C.c_int32), ('reserved', C.c_int32),
+    _fields_ = [('n_ranks', C.c_int32), ('rank', C.c_int32), ('halo', C.c_int32), ('occ_words', C.c_int32),
                 ('view0', C.c_int64), ('n_views_total', C.c_int64), ('local_stack', C.c_void_p),
-                ('band_stack', C.c_void_p * VS_MAX_RANKS)]
+                ('band_stack', C.c_void_p * VS_MAX_RANKS), ('occ', C.c_void_p * VS_MAX_RANKS)]
 
 
 _vp = C.c_void_p
@@ -82,6 +86,8 @@ SIGNATURES = {
     'vs_peer_close': (C.c_int, [_vp, _vp]),
     'vs_peer_free': (C.c_int, [_vp, _vp]),
     'vs_set_exchange': (C.c_int, [_vp, C.POINTER(vs_exchange)]),
+    'vs_set_occupancy': (C.c_int, [_vp, _vp, _i32, _vp, _i64]),
+    'vs_fuse_views_sparse': (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _vp]),
 }
 
 

@@ -138,6 +138,12 @@ int vs_ctx_create(int device, vs_ctx** out) {
     ctx->timing = false;
     ctx->xch_on = false;
     memset(&ctx->xch, 0, sizeof(ctx->xch));
+    ctx->occ = nullptr;
+    ctx->occ_words = 0;
+    ctx->occ_stack_base = nullptr;
+    ctx->occ_view0 = 0;
+    ctx->d_fuse_plan = nullptr;
+    ctx->fuse_plan_ints = 0;
     for (int i = 0; i < VS_MAX_STREAMS; ++i) {
         ctx->side_stream[i] = nullptr;
         ctx->join_event[i] = nullptr;
@@ -167,6 +173,7 @@ int vs_ctx_destroy(vs_ctx* ctx) {
     VsDeviceGuard guard(ctx->device);
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     if (ctx->d_exact) cudaFree(ctx->d_exact);
+    if (ctx->d_fuse_plan) cudaFree(ctx->d_fuse_plan);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     for (int i = 0; i < VS_MAX_STREAMS; ++i) {
         if (ctx->side_stream[i]) cudaStreamDestroy(ctx->side_stream[i]);

@@ -25,13 +25,20 @@ bool vs_peer_plan_for(const vs_ctx* ctx, const float* plane, int64_t plane_strid
     plan->halo = x.halo;
     plan->inv = (unsigned)((((unsigned long long)x.n_ranks) << 32) / (unsigned long long)H);
     vs_band_rows(H, x.n_ranks, plan->row0);
-    for (int j = 0; j < VS_MAX_RANKS; ++j) plan->plane[j] = nullptr;
+    for (int j = 0; j < VS_MAX_RANKS; ++j) {
+        plan->plane[j] = nullptr;
+        plan->occ[j] = nullptr;
+    }
+    plan->occ_words = x.occ_words;
+    plan->tiles_x = (W + VS_TILE_W - 1) / VS_TILE_W;
+    plan->view = (int)g;
     for (int j = 0; j < x.n_ranks; ++j) {
         const int r0 = plan->row0[j], r1 = plan->row0[j + 1];
         if (r1 == r0) continue;
         const int h0 = r0 - x.halo > 0 ? r0 - x.halo : 0;
         const int h1 = r1 + x.halo < H ? r1 + x.halo : H;
         plan->plane[j] = x.band_stack[j] + (size_t)g * (size_t)(h1 - h0) * (size_t)W;
+        if (x.occ_words > 0) plan->occ[j] = x.occ[j];
     }
     return true;
 }
@@ -108,8 +115,29 @@ int vs_set_exchange(vs_ctx* ctx, const vs_exchange* ex) {
     vs_band_rows(ctx->aoi.ysize, ex->n_ranks, row0);
     for (int j = 0; j < ex->n_ranks; ++j)
         VS_REQUIRE(row0[j + 1] == row0[j] || ex->band_stack[j] != nullptr, "vs_set_exchange: NULL band_stack of a rank with rows");
+    VS_REQUIRE(ex->occ_words >= 0, "vs_set_exchange: negative occ_words");
+    if (ex->occ_words > 0) {
+        VS_REQUIRE((int64_t)ex->occ_words * 32 >= ex->n_views_total, "vs_set_exchange: occ_words too small for n_views_total");
+        for (int j = 0; j < ex->n_ranks; ++j)
+            VS_REQUIRE(row0[j + 1] == row0[j] || ex->occ[j] != nullptr, "vs_set_exchange: NULL occupancy bitmap of a rank with rows");
+    }
     ctx->xch = *ex;
     ctx->xch_on = true;
+    return VS_OK;
+}
+
+int vs_set_occupancy(vs_ctx* ctx, uint32_t* occ, int32_t occ_words, const float* stack_base, int64_t view0) {
+    VS_REQUIRE(ctx != nullptr, "vs_set_occupancy: NULL context");
+    if (occ == nullptr) {
+        ctx->occ = nullptr;
+        ctx->occ_words = 0;
+        return VS_OK;
+    }
+    VS_REQUIRE(occ_words > 0 && stack_base != nullptr && view0 >= 0, "vs_set_occupancy: bad argument");
+    ctx->occ = occ;
+    ctx->occ_words = occ_words;
+    ctx->occ_stack_base = stack_base;
+    ctx->occ_view0 = view0;
     return VS_OK;
 }
 

@@ -30,7 +30,7 @@ __device__ __forceinline__ void write_nan_tile(float* __restrict__ blur_out, T* 
         if (gy < H && gx < W) {
             if (blur_out != nullptr) {
                 blur_out[(size_t)gy * W + gx] = CUDART_NAN_F;
-                sink.store1(gy, gx, W, CUDART_NAN_F);
+                if (!sink.skips_empty_tiles()) sink.store1(gy, gx, W, CUDART_NAN_F);
             }
             if (filled_out != nullptr) filled_out[(size_t)gy * W + gx] = (T)CUDART_NAN;
             ++n;
@@ -179,6 +179,7 @@ k_grid_finalize(const Key* __restrict__ keygrid, int W, int H, typename KeyTrait
             }
         }
     }
+    if (tid == 0 && blur_out != nullptr) sink.mark_tile(blockIdx.x, blockIdx.y, H);   // this (tile, view) holds data
     __syncthreads();
 
     // 2. hole fill: NaN cell <- median of its non-NaN 3x3 neighbours in the PRE-fill grid, dense over the list.
@@ -325,6 +326,21 @@ int vs_grid_finalize_peer(vs_ctx* ctx, const uint32_t* keygrid, int xsize, int y
                                                                       reinterpret_cast<unsigned long long*>(nan_count),
                                                                       sink);
     VS_CHECK_LAUNCH(ctx, "k_grid_finalize<u32, peer>");
+    return VS_OK;
+}
+
+// Stage B of one view that also records the tile occupancy of the plane (vs_set_occupancy; called by vs_views_to_dsm).
+int vs_grid_finalize_occ(vs_ctx* ctx, const uint32_t* keygrid, int xsize, int ysize, float* dsm_out, int simd_lanes,
+                         uint64_t* nan_count, const VsOccPlan& plan, cudaStream_t stream) {
+    if (nan_count) VS_CUDA(cudaMemsetAsync(nan_count, 0, sizeof(uint64_t), stream));
+    OccSink sink;
+    sink.o = plan;
+    dim3 grid((xsize + TW - 1) / TW, (ysize + TH - 1) / TH);
+    k_grid_finalize<uint32_t, OccSink><<<grid, kThreads, 0, stream>>>(keygrid, xsize, ysize, nullptr, dsm_out,
+                                                                     simd_cols_for(xsize, simd_lanes),
+                                                                     reinterpret_cast<unsigned long long*>(nan_count),
+                                                                     sink);
+    VS_CHECK_LAUNCH(ctx, "k_grid_finalize<u32, occ>");
     return VS_OK;
 }
 

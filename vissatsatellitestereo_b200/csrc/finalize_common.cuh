@@ -79,9 +79,34 @@ __device__ __forceinline__ float median9_exact(const float* r0, const float* r1,
 struct NoSink {
     __device__ __forceinline__ void store4(int, int, int, const float4&) const {}
     __device__ __forceinline__ void store1(int, int, int, float) const {}
+    __device__ __forceinline__ void mark_tile(int, int, int) const {}       // one thread per CTA calls it
+    __device__ __forceinline__ bool skips_empty_tiles() const { return false; }
+};
+// Records which (tile, view) pairs hold data (vs_set_occupancy); no peer stores.
+struct OccSink {
+    VsOccPlan o;
+    __device__ __forceinline__ void store4(int, int, int, const float4&) const {}
+    __device__ __forceinline__ void store1(int, int, int, float) const {}
+    __device__ __forceinline__ void mark_tile(int tx, int ty, int) const {
+        atomicOr(o.occ + ((size_t)ty * o.tiles_x + tx) * o.occ_words + (o.view >> 5), 1u << (o.view & 31));
+    }
+    __device__ __forceinline__ bool skips_empty_tiles() const { return false; }
 };
 struct PeerSink {
     VsPeerPlan p;
+    // sparse exchange: an all-empty tile is not stored into the band stacks; a tile with data sets its (tile, view)
+    // bit in the bitmap of every rank whose band (+ halo) it touches (system-scope atomics over NVLink)
+    __device__ __forceinline__ bool skips_empty_tiles() const { return p.occ_words > 0; }
+    __device__ __forceinline__ void mark_tile(int tx, int ty, int H) const {
+        if (p.occ_words <= 0) return;
+        const int y0 = ty * TH, y1 = min(y0 + TH, H) - 1;
+        const int j0 = max(band_of(y0) - 1, 0), j1 = min(band_of(y1) + 1, p.n - 1);
+        for (int j = j0; j <= j1; ++j) {
+            if (p.row0[j + 1] == p.row0[j] || p.occ[j] == nullptr) continue;
+            if (y1 >= p.row0[j] - p.halo && y0 < p.row0[j + 1] + p.halo)
+                atomicOr_system(p.occ[j] + ((size_t)ty * p.tiles_x + tx) * p.occ_words + (p.view >> 5), 1u << (p.view & 31));
+        }
+    }
     // band j of row y: row0[j] <= y < row0[j+1].  Bands are near-uniform (numpy.array_split), so y*n/H is at most
     // one band off; the two loops make it exact (and step over empty bands when H < n).
     __device__ __forceinline__ int band_of(int y) const {

@@ -17,6 +17,8 @@
 // V > 128:  k_fuse_large  -- 4, 8 or 32 threads per cell, sorted runs in shared memory, bitwise bisection.
 #include <math_constants.h>
 
+#include <algorithm>
+
 #include "sortnets_gen.cuh"
 #include "vs_common.cuh"
 
@@ -324,9 +326,19 @@ __device__ __forceinline__ void group_select(const uint32_t* __restrict__ run, i
 
 // nanmean of the survivors of one cell in numpy's pairwise order, computed by the LANES threads of the cell's group
 // (lane j < 8 owns numpy's accumulator r[j]); the views are re-read from L2.  Every lane returns the mean.
-template <int LANES>
+// `present(v)`: whether view v takes part at all (dense stacks: always; sparse fusion: the tile's occupancy bit -- an
+// absent view counts as NaN, contributes +0 to the sum like any rejected value, and its memory is never read).
+struct AllPresent {
+    __device__ __forceinline__ bool operator()(int) const { return true; }
+};
+struct BitsPresent {
+    const uint32_t* bits;   // shared memory: the tile's occupancy words
+    __device__ __forceinline__ bool operator()(int v) const { return (bits[v >> 5] >> (v & 31)) & 1u; }
+};
+
+template <int LANES, typename Present>
 __device__ __forceinline__ float sum_survivors(const float* __restrict__ views, int64_t cell, int64_t plane_stride, int V,
-                                               float med, float mad, int lane, unsigned gmask) {
+                                               float med, float mad, int lane, unsigned gmask, const Present& present) {
     const KeepFn y{views + cell, plane_stride, med, mad};
     // numpy's 8 strided accumulators r[0..7] are spread over the first AL = min(LANES, 8) lanes of the group:
     // lane q < AL owns r[q], r[q + AL], ...
@@ -360,6 +372,7 @@ __device__ __forceinline__ float sum_survivors(const float* __restrict__ views, 
             if (n < 8) {
                 leaf = 0.0f;
                 for (int i = 0; i < n; ++i) {   // every lane computes the same value
+                    if (!present(off + i)) continue;
                     leaf = __fadd_rn(leaf, y(off + i));
                     if (lane == 0) cnt += y.kept(off + i);
                 }
@@ -371,14 +384,16 @@ __device__ __forceinline__ float sum_survivors(const float* __restrict__ views, 
                 if (acc_lane) {   // every view index of the leaf's full blocks is visited exactly once: count here too
 #pragma unroll
                     for (int m = 0; m < ACC; ++m) {
-                        const float* q = y.p + (int64_t)(off + lane + m * AL) * y.stride;
+                        const int v0 = off + lane + m * AL;
+                        const float* q = y.p + (int64_t)v0 * y.stride;
                         const int64_t step8 = 8 * y.stride;
-                        float t = __ldg(q);
+                        float t = present(v0) ? __ldg(q) : CUDART_NAN_F;
                         bool keep = (t == t) && !(fabsf(__fsub_rn(t, y.med)) > y.mad);
                         r[m] = keep ? t : 0.0f;
                         cnt += keep;
                         for (int i = 8; i < nfull; i += 8) {
                             q += step8;
+                            if (!present(v0 + i)) continue;       // + 0: no-op
                             t = __ldg(q);
                             keep = (t == t) && !(fabsf(__fsub_rn(t, y.med)) > y.mad);
                             r[m] = __fadd_rn(r[m], keep ? t : 0.0f);
@@ -394,6 +409,7 @@ __device__ __forceinline__ float sum_survivors(const float* __restrict__ views, 
                 leaf = __fadd_rn(__fadd_rn(__fadd_rn(a8[0], a8[1]), __fadd_rn(a8[2], a8[3])),
                                  __fadd_rn(__fadd_rn(a8[4], a8[5]), __fadd_rn(a8[6], a8[7])));
                 for (int i = nfull; i < n; ++i) {
+                    if (!present(off + i)) continue;
                     leaf = __fadd_rn(leaf, y(off + i));
                     if (lane == 0) cnt += y.kept(off + i);
                 }
@@ -487,8 +503,319 @@ k_fuse_large(const float* __restrict__ views, int64_t plane_stride, int V, int64
     const float mad = __fdiv_rn(__fadd_rn(vs_unkey32(klo), vs_unkey32(khi)), 2.0f);
 
     // 5. nanmean of the survivors in numpy's pairwise order
-    const float mean = sum_survivors<LANES>(views, cell, plane_stride, V, med, mad, lane, gmask);
+    const float mean = sum_survivors<LANES>(views, cell, plane_stride, V, med, mad, lane, gmask, AllPresent());
     if (lane == 0) out[cell] = mean;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Sparse fusion (vs_fuse_views_sparse): large AOIs, where a view covers a fraction of the grid.
+//
+// Stage B records per 64x32 tile which views hold data there (occupancy bitmap, vs_set_occupancy / vs_exchange.occ).
+// A planning kernel bins the tiles by their view count; one kernel per bin then runs the register-network path
+// (or the multi-lane path above 128 views) over that bin's tiles, gathering only the marked planes: an unmarked
+// (tile, view) pair is NaN by definition and its memory is never read.  The survivors are summed in numpy's order
+// over the ORIGINAL view axis (the tree depends on V and on the view indices, not on how many views are present),
+// with absent views skipped -- they would add +0.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kSparseBins = 19;
+__constant__ int c_bin_cap[kSparseBins] = {8, 16, 24, 32, 40, 48, 56, 64, 80, 96, 112, 128, 160, 208, 256, 416, 512, 1024, 2048};
+static const int h_bin_cap[kSparseBins] = {8, 16, 24, 32, 40, 48, 56, 64, 80, 96, 112, 128, 160, 208, 256, 416, 512, 1024, 2048};
+constexpr int kMaxOccWords = 64;   // 2048 views
+
+struct SparseGeom {
+    const float* views;
+    int64_t plane_stride;
+    int V, rows, W, row0;      // planes hold grid rows [row0, row0 + rows)
+    const uint32_t* occ;
+    int occ_words, tiles_x;
+    int ty_first, n_units;     // tile rows ty_first .. ; units = tile rows x tile columns
+    const int* bin_count;      // [kSparseBins]
+    const int* bin_list;       // [kSparseBins][n_units]
+    float* out;
+};
+
+__global__ void k_fuse_plan(const uint32_t* __restrict__ occ, int occ_words, int tiles_x, int ty_first, int n_units,
+                            int* __restrict__ bin_count, int* __restrict__ bin_list) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n_units) return;
+    const int ty = ty_first + u / tiles_x, tx = u - (u / tiles_x) * tiles_x;
+    const uint32_t* w = occ + ((size_t)ty * tiles_x + tx) * occ_words;
+    int n = 0;
+    for (int i = 0; i < occ_words; ++i) n += __popc(w[i]);
+    int b = 0;
+    while (b < kSparseBins - 1 && n > c_bin_cap[b]) ++b;
+    bin_list[(size_t)b * n_units + atomicAdd(bin_count + b, 1)] = u;
+}
+
+// One warp turns the tile's occupancy words into the ascending list of its views (shared memory).
+__device__ __forceinline__ int build_view_list(const uint32_t* __restrict__ occ_tile, int occ_words, uint32_t* s_bits,
+                                               int* s_list, int cap) {
+    __shared__ int s_n;
+    const int tid = threadIdx.x;
+    if (tid < 32) {
+        int base = 0;
+        for (int w0 = 0; w0 < occ_words; w0 += 32) {
+            const int w = w0 + tid;
+            const uint32_t bits = w < occ_words ? occ_tile[w] : 0u;
+            if (w < kMaxOccWords) s_bits[w] = bits;
+            const int c = __popc(bits);
+            int incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (tid >= o) incl += t;
+            }
+            int pos = base + incl - c;
+            uint32_t b = bits;
+            while (b) {
+                const int bit = __ffs(b) - 1;
+                b &= b - 1;
+                if (pos < cap) s_list[pos] = w * 32 + bit;
+                ++pos;
+            }
+            base += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (tid == 0) s_n = base;
+    }
+    __syncthreads();
+    return s_n;
+}
+
+// numpy's pairwise sum over the original view axis [0, V), one thread per cell, absent views skipped
+template <typename Present>
+__device__ __forceinline__ float leaf_sum_1t(const KeepFn& y, const Present& present, int off, int n, int& cnt) {
+    if (n < 8) {
+        float res = 0.0f;
+        for (int i = 0; i < n; ++i)
+            if (present(off + i)) {
+                res = __fadd_rn(res, y(off + i));
+                cnt += y.kept(off + i);
+            }
+        return res;
+    }
+    float r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        r[j] = 0.0f;
+        if (present(off + j)) {
+            r[j] = y(off + j);
+            cnt += y.kept(off + j);
+        }
+    }
+    const int nfull = n - (n & 7);
+    for (int i = 8; i < nfull; i += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (present(off + i + j)) {
+                r[j] = __fadd_rn(r[j], y(off + i + j));
+                cnt += y.kept(off + i + j);
+            }
+    }
+    float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                          __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+    for (int i = nfull; i < n; ++i)
+        if (present(off + i)) {
+            res = __fadd_rn(res, y(off + i));
+            cnt += y.kept(off + i);
+        }
+    return res;
+}
+
+template <typename Present>
+__device__ __forceinline__ float sum_survivors_1t(const KeepFn& y, const Present& present, int V) {
+    int cnt = 0;
+    float total;
+    if (V <= 128) {
+        total = leaf_sum_1t(y, present, 0, V, cnt);
+    } else {   // numpy's recursion tree, walked left to right with an explicit stack (as sum_survivors above)
+        float stack_val[12];
+        int stack_lvl[12];
+        int sp = 0;
+        int seg_off[12], seg_n[12], seg_lvl[12];
+        int tp = 1;
+        seg_off[0] = 0; seg_n[0] = V; seg_lvl[0] = 0;
+        while (tp > 0) {
+            --tp;
+            const int off = seg_off[tp], n = seg_n[tp], lvl = seg_lvl[tp];
+            if (n > 128) {
+                int n2 = n >> 1;
+                n2 -= n2 & 7;
+                seg_off[tp] = off + n2; seg_n[tp] = n - n2; seg_lvl[tp] = lvl + 1; ++tp;
+                seg_off[tp] = off; seg_n[tp] = n2; seg_lvl[tp] = lvl + 1; ++tp;
+                continue;
+            }
+            float val = leaf_sum_1t(y, present, off, n, cnt);
+            int l = lvl;
+            while (sp > 0 && stack_lvl[sp - 1] == l) {
+                val = __fadd_rn(stack_val[sp - 1], val);
+                --sp;
+                --l;
+            }
+            stack_val[sp] = val;
+            stack_lvl[sp] = l;
+            ++sp;
+        }
+        total = stack_val[0];
+    }
+    return __fdiv_rn(total, (float)cnt);
+}
+
+// rows of unit u (a tile clipped to the planes' rows), split into 4 slabs of 8 tile rows
+__device__ __forceinline__ void unit_geometry(const SparseGeom& g, int u, int& ty, int& tx) {
+    ty = g.ty_first + u / g.tiles_x;
+    tx = u - (u / g.tiles_x) * g.tiles_x;
+}
+
+template <int NV>
+__global__ void __launch_bounds__(kBlockSmall, (NV > 64 && NV <= 112) ? 4 : 1)
+k_fuse_sparse_regs(const __grid_constant__ SparseGeom g, int bin) {
+    __shared__ uint32_t s_bits[kMaxOccWords];
+    __shared__ int s_list[NV];
+    const int n_items = g.bin_count[bin] * 4;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int u = g.bin_list[(size_t)bin * g.n_units + (item >> 2)];
+        int ty, tx;
+        unit_geometry(g, u, ty, tx);
+        __syncthreads();   // the previous item's readers of s_list / s_bits are done
+        const int n = build_view_list(g.occ + ((size_t)ty * g.tiles_x + tx) * g.occ_words, g.occ_words, s_bits, s_list, NV);
+        const int gy0 = max(ty * VS_TILE_H + (item & 3) * 8, g.row0);
+        const int gy1 = min(min(ty * VS_TILE_H + (item & 3) * 8 + 8, g.row0 + g.rows), (ty + 1) * VS_TILE_H);
+        const BitsPresent present{s_bits};
+        for (int c = threadIdx.x; c < VS_TILE_W * (gy1 - gy0); c += kBlockSmall) {
+            const int gy = gy0 + (c >> 6), gx = tx * VS_TILE_W + (c & 63);
+            if (gx >= g.W) continue;
+            const int64_t cell = (int64_t)(gy - g.row0) * g.W + gx;
+            float s[NV];
+            int k = 0;
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                float t = CUDART_NAN_F;
+                if (i < n) t = __ldg(g.views + (int64_t)s_list[i] * g.plane_stride + cell);
+                const bool ok = (t == t);
+                k += ok;
+                s[i] = ok ? t : CUDART_INF_F;
+            }
+            if (k <= 2) {  // aggregate_2p5d.py:69-71
+                g.out[cell] = CUDART_NAN_F;
+                continue;
+            }
+            SortNet<NV>::sort(s);
+            const float med = middle_of_sorted<NV>(s, k);
+#pragma unroll
+            for (int i = 0; i < NV; ++i) s[i] = fabsf(__fsub_rn(s[i], med));
+            bitonic_merge_regs<NV>(s);
+            const float mad = middle_of_sorted<NV>(s, k);
+            const KeepFn y{g.views + cell, g.plane_stride, med, mad};
+            g.out[cell] = sum_survivors_1t(y, present, g.V);
+        }
+    }
+}
+
+// More than 128 views in a tile: the multi-lane path of k_fuse_large over the tile's view list.
+template <int LANES, int NVL>
+__global__ void __launch_bounds__(kLargeThreads)
+k_fuse_sparse_large(const __grid_constant__ SparseGeom g, int bin, int VS) {
+    constexpr int CELLS = kLargeThreads / LANES;   // cells per pass: 64, 32 or 8 consecutive columns of one tile row
+    constexpr int PASSES_PER_ROW = VS_TILE_W / CELLS;
+    extern __shared__ uint32_t s_tile[];           // CELLS x VS words
+    __shared__ uint32_t s_bits[kMaxOccWords];
+    __shared__ int s_list[LANES * NVL];
+    const int tid = threadIdx.x;
+    const int n_items = g.bin_count[bin] * 4;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int u = g.bin_list[(size_t)bin * g.n_units + (item >> 2)];
+        int ty, tx;
+        unit_geometry(g, u, ty, tx);
+        __syncthreads();
+        const int n = build_view_list(g.occ + ((size_t)ty * g.tiles_x + tx) * g.occ_words, g.occ_words, s_bits, s_list,
+                                      LANES * NVL);
+        const int gy0 = max(ty * VS_TILE_H + (item & 3) * 8, g.row0);
+        const int gy1 = min(min(ty * VS_TILE_H + (item & 3) * 8 + 8, g.row0 + g.rows), (ty + 1) * VS_TILE_H);
+        const BitsPresent present{s_bits};
+        for (int pass = 0; pass < (gy1 - gy0) * PASSES_PER_ROW; ++pass) {
+            const int gy = gy0 + pass / PASSES_PER_ROW;
+            const int gx0 = tx * VS_TILE_W + (pass % PASSES_PER_ROW) * CELLS;
+            if (gx0 >= g.W) continue;                       // block-uniform
+            const int64_t cell0 = (int64_t)(gy - g.row0) * g.W + gx0;
+            const int n_cols = min(CELLS, g.W - gx0);
+            __syncthreads();                                // previous pass done with s_tile
+            for (int i = tid; i < CELLS * n; i += kLargeThreads) {
+                const int slot = i / CELLS, c = i - slot * CELLS;
+                float t = CUDART_NAN_F;
+                if (c < n_cols) t = __ldg(g.views + (int64_t)s_list[slot] * g.plane_stride + cell0 + c);
+                s_tile[c * VS + slot] = __float_as_uint(t);
+            }
+            __syncthreads();
+            const int c_local = tid / LANES, lane = tid % LANES;
+            const int64_t cell = cell0 + c_local;
+            const unsigned gmask = LANES == 32 ? 0xffffffffu : (((1u << LANES) - 1u) << ((tid & 31) / LANES * LANES));
+            uint32_t* run = s_tile + c_local * VS + lane;
+            float s[NVL];
+            int k_lane = 0;
+#pragma unroll
+            for (int i = 0; i < NVL; ++i) {
+                const int slot = lane + i * LANES;
+                float t = CUDART_INF_F;
+                if (slot < n) {
+                    const float x = __uint_as_float(run[i * LANES]);
+                    if (x == x) {
+                        t = x;
+                        ++k_lane;
+                    }
+                }
+                s[i] = t;
+            }
+            const int k = group_sum<LANES>(k_lane, gmask);
+            if (c_local >= n_cols) continue;     // whole group skips together (no block barrier below)
+            if (k <= 2) {
+                if (lane == 0) g.out[cell] = CUDART_NAN_F;
+                continue;
+            }
+            SortNet<NVL>::sort(s);
+#pragma unroll
+            for (int i = 0; i < NVL; ++i) run[i * LANES] = vs_key32(s[i]);
+#pragma unroll
+            for (int i = NVL; i < RunPad<NVL>::value; ++i) run[i * LANES] = 0xffffffffu;
+            __syncwarp(gmask);
+            const int ilo = (k - 1) >> 1, ihi = k >> 1;
+            uint32_t khi, klo;
+            group_select<LANES, NVL>(run, ihi, ilo != ihi, gmask, 0u, 31, khi, klo);
+            const float med = __fdiv_rn(__fadd_rn(vs_unkey32(klo), vs_unkey32(khi)), 2.0f);
+            __syncwarp(gmask);
+#pragma unroll
+            for (int i = 0; i < NVL; ++i) s[i] = fabsf(__fsub_rn(s[i], med));
+            bitonic_merge_regs<NVL>(s);
+#pragma unroll
+            for (int i = 0; i < NVL; ++i) run[i * LANES] = vs_key32(s[i]);
+            __syncwarp(gmask);
+            group_select<LANES, NVL>(run, ihi, ilo != ihi, gmask, 0x80000000u, 30, khi, klo);
+            const float mad = __fdiv_rn(__fadd_rn(vs_unkey32(klo), vs_unkey32(khi)), 2.0f);
+            const float mean = sum_survivors<LANES>(g.views, cell, g.plane_stride, g.V, med, mad, lane, gmask, present);
+            if (lane == 0) g.out[cell] = mean;
+        }
+    }
+}
+
+template <int NV>
+int launch_sparse_regs(vs_ctx* ctx, const SparseGeom& g, int bin, cudaStream_t stream) {
+    // persistent grid: the number of tiles of this bin is only known on the device
+    const int blocks = std::min(g.n_units * 4, ctx->sm_count * 8);
+    k_fuse_sparse_regs<NV><<<blocks, kBlockSmall, 0, stream>>>(g, bin);
+    VS_CHECK_LAUNCH(ctx, "k_fuse_sparse_regs");
+    return VS_OK;
+}
+
+template <int LANES, int NVL>
+int launch_sparse_large(vs_ctx* ctx, const SparseGeom& g, int bin, cudaStream_t stream) {
+    constexpr int CELLS = kLargeThreads / LANES;
+    int VS = LANES * RunPad<NVL>::value;
+    VS += (9 - (VS & 31) + 32) & 31;
+    const size_t smem = (size_t)CELLS * VS * sizeof(uint32_t);
+    VS_CUDA(cudaFuncSetAttribute(k_fuse_sparse_large<LANES, NVL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int blocks = std::min(g.n_units * 4, ctx->sm_count * 4);
+    k_fuse_sparse_large<LANES, NVL><<<blocks, kLargeThreads, smem, stream>>>(g, bin, VS);
+    VS_CHECK_LAUNCH(ctx, "k_fuse_sparse_large");
+    return VS_OK;
 }
 
 template <int NV>
@@ -582,3 +909,78 @@ extern "C" int vs_fuse_views(vs_ctx* ctx, const float* views, int64_t plane_stri
     return launch_large(ctx, views, plane_stride, V, n_cells, out_mean, stream);
 }
 
+
+extern "C" int vs_fuse_views_sparse(vs_ctx* ctx, const float* views, int64_t plane_stride, int32_t n_views, int32_t rows,
+                                    int32_t W, int32_t row0, const uint32_t* occ, int32_t occ_words, float* out_mean,
+                                    void* stream_) {
+    VS_REQUIRE(ctx != nullptr, "vs_fuse_views_sparse: NULL context");
+    VS_REQUIRE(n_views >= 1 && n_views <= 2048, "vs_fuse_views_sparse: n_views must be 1..2048");
+    VS_REQUIRE(rows >= 0 && W >= 0 && row0 >= 0, "vs_fuse_views_sparse: negative size");
+    const int64_t n_cells = (int64_t)rows * W;
+    if (n_cells == 0) return VS_OK;
+    VS_REQUIRE(views != nullptr && out_mean != nullptr && occ != nullptr, "vs_fuse_views_sparse: NULL array");
+    VS_REQUIRE(plane_stride >= n_cells, "vs_fuse_views_sparse: plane_stride smaller than a plane");
+    VS_REQUIRE(occ_words > 0 && occ_words <= kMaxOccWords && (int64_t)occ_words * 32 >= n_views,
+               "vs_fuse_views_sparse: occ_words must cover n_views (and at most 2048 views)");
+    VsDeviceGuard guard(ctx->device);
+    if (!guard.ok) return vs_cuda_fail(cudaGetLastError(), "cudaSetDevice");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SparseGeom g;
+    g.views = views;
+    g.plane_stride = plane_stride;
+    g.V = n_views;
+    g.rows = rows;
+    g.W = W;
+    g.row0 = row0;
+    g.occ = occ;
+    g.occ_words = occ_words;
+    g.tiles_x = (W + VS_TILE_W - 1) / VS_TILE_W;
+    g.ty_first = row0 / VS_TILE_H;
+    const int ty_last = (row0 + rows - 1) / VS_TILE_H;
+    g.n_units = (ty_last - g.ty_first + 1) * g.tiles_x;
+    g.out = out_mean;
+    // scratch: per-bin counters + per-bin unit lists (grown outside of stream capture: the first call sizes it)
+    const size_t need = (size_t)kSparseBins * (1 + (size_t)g.n_units);
+    if (ctx->fuse_plan_ints < need) {
+        if (ctx->d_fuse_plan) cudaFree(ctx->d_fuse_plan);
+        ctx->d_fuse_plan = nullptr;
+        ctx->fuse_plan_ints = 0;
+        VS_CUDA(cudaMalloc(&ctx->d_fuse_plan, need * sizeof(int)));
+        ctx->fuse_plan_ints = need;
+    }
+    int* bin_count = ctx->d_fuse_plan;
+    int* bin_list = ctx->d_fuse_plan + kSparseBins;
+    g.bin_count = bin_count;
+    g.bin_list = bin_list;
+    VS_CUDA(cudaMemsetAsync(bin_count, 0, kSparseBins * sizeof(int), stream));
+    k_fuse_plan<<<(g.n_units + 255) / 256, 256, 0, stream>>>(occ, occ_words, g.tiles_x, g.ty_first, g.n_units, bin_count,
+                                                             bin_list);
+    VS_CHECK_LAUNCH(ctx, "k_fuse_plan");
+    // one launch per bin that this view count can reach (a tile never has more than n_views views)
+    int rc = VS_OK;
+    for (int b = 0; b < kSparseBins && rc == VS_OK; ++b) {
+        if (b > 0 && h_bin_cap[b - 1] >= n_views) break;
+        switch (b) {
+            case 0: rc = launch_sparse_regs<8>(ctx, g, b, stream); break;
+            case 1: rc = launch_sparse_regs<16>(ctx, g, b, stream); break;
+            case 2: rc = launch_sparse_regs<24>(ctx, g, b, stream); break;
+            case 3: rc = launch_sparse_regs<32>(ctx, g, b, stream); break;
+            case 4: rc = launch_sparse_regs<40>(ctx, g, b, stream); break;
+            case 5: rc = launch_sparse_regs<48>(ctx, g, b, stream); break;
+            case 6: rc = launch_sparse_regs<56>(ctx, g, b, stream); break;
+            case 7: rc = launch_sparse_regs<64>(ctx, g, b, stream); break;
+            case 8: rc = launch_sparse_regs<80>(ctx, g, b, stream); break;
+            case 9: rc = launch_sparse_regs<96>(ctx, g, b, stream); break;
+            case 10: rc = launch_sparse_regs<112>(ctx, g, b, stream); break;
+            case 11: rc = launch_sparse_regs<128>(ctx, g, b, stream); break;
+            case 12: rc = launch_sparse_large<4, 40>(ctx, g, b, stream); break;
+            case 13: rc = launch_sparse_large<4, 52>(ctx, g, b, stream); break;
+            case 14: rc = launch_sparse_large<4, 64>(ctx, g, b, stream); break;
+            case 15: rc = launch_sparse_large<8, 52>(ctx, g, b, stream); break;
+            case 16: rc = launch_sparse_large<8, 64>(ctx, g, b, stream); break;
+            case 17: rc = launch_sparse_large<32, 32>(ctx, g, b, stream); break;
+            case 18: rc = launch_sparse_large<32, 64>(ctx, g, b, stream); break;
+        }
+    }
+    return rc;
+}

@@ -4,6 +4,8 @@
 bool vs_peer_plan_for(const vs_ctx* ctx, const float* plane, int64_t plane_stride, VsPeerPlan* plan);
 int vs_grid_finalize_peer(vs_ctx* ctx, const uint32_t* keygrid, int xsize, int ysize, float* dsm_out, int simd_lanes,
                           uint64_t* nan_count, const VsPeerPlan& plan, cudaStream_t stream);
+int vs_grid_finalize_occ(vs_ctx* ctx, const uint32_t* keygrid, int xsize, int ysize, float* dsm_out, int simd_lanes,
+                         uint64_t* nan_count, const VsOccPlan& plan, cudaStream_t stream);
 
 extern "C" {
 
@@ -80,6 +82,20 @@ int vs_views_to_dsm(vs_ctx* ctx, int32_t n_views, const float* const* depth, con
                 break;
             }
             rc = vs_grid_finalize_peer(ctx, kg, xs, ys, plane, simd_lanes, nan_counts ? nan_counts + v : nullptr, plan, st);
+        } else if (ctx->occ != nullptr) {   // record which tiles of this plane hold data (vs_set_occupancy)
+            const ptrdiff_t d = plane - ctx->occ_stack_base;
+            const int64_t g = ctx->occ_view0 + (plane_stride > 0 ? d / plane_stride : 0);
+            if (d < 0 || d % plane_stride != 0 || g < 0 || g >= (int64_t)ctx->occ_words * 32) {
+                vs_set_error("vs_views_to_dsm: dsm_stack plane is outside the stack given to vs_set_occupancy");
+                rc = VS_ERR_INVALID;
+                break;
+            }
+            VsOccPlan op;
+            op.occ = ctx->occ;
+            op.occ_words = ctx->occ_words;
+            op.tiles_x = (xs + VS_TILE_W - 1) / VS_TILE_W;
+            op.view = (int)g;
+            rc = vs_grid_finalize_occ(ctx, kg, xs, ys, plane, simd_lanes, nan_counts ? nan_counts + v : nullptr, op, st);
         } else {
             rc = vs_grid_finalize(ctx, kg, xs, ys, plane, simd_lanes, nan_counts ? nan_counts + v : nullptr, st);
         }

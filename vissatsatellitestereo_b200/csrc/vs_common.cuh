@@ -49,6 +49,15 @@ struct VsPeerPlan {
     unsigned inv;                    // floor(2^32 * n / H): y * inv >> 32 ~ band of row y
     int row0[VS_MAX_RANKS + 1];      // band boundaries; row0[n] = H
     float* plane[VS_MAX_RANKS];
+    // sparse exchange: occupancy bitmaps of the ranks (nullptr = dense exchange: empty tiles are stored as NaN)
+    uint32_t* occ[VS_MAX_RANKS];
+    int occ_words, tiles_x, view;    // words per tile, tile columns, global view index of this plane
+};
+
+// Local occupancy marking of stage B (vs_set_occupancy), passed by value to k_grid_finalize.
+struct VsOccPlan {
+    uint32_t* occ;
+    int occ_words, tiles_x, view;
 };
 
 struct vs_ctx {
@@ -77,6 +86,14 @@ struct vs_ctx {
     // peer-store exchange of stage B (exchange.cu)
     bool xch_on;
     vs_exchange xch;
+    // occupancy marking without an exchange (vs_set_occupancy)
+    uint32_t* occ;
+    int occ_words;
+    const float* occ_stack_base;
+    int64_t occ_view0;
+    // scratch of vs_fuse_views_sparse: per-bin tile lists (fuse.cu)
+    int* d_fuse_plan;
+    size_t fuse_plan_ints;
     bool timing;
     std::vector<cudaEvent_t> ev_pool;   // 3 events per logged view: before A, between A and B, after B
     size_t ev_used;

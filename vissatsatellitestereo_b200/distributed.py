@@ -151,8 +151,8 @@ class _DeviceArray:
     """Device memory owned by libvissat_b200 (vs_peer_alloc / vs_peer_open) exposed through
     __cuda_array_interface__ so that torch can wrap it without a copy."""
 
-    def __init__(self, ptr, shape):
-        self.__cuda_array_interface__ = {'shape': tuple(int(x) for x in shape), 'typestr': '<f4', 'data': (int(ptr), False),
+    def __init__(self, ptr, shape, typestr='<f4'):
+        self.__cuda_array_interface__ = {'shape': tuple(int(x) for x in shape), 'typestr': typestr, 'data': (int(ptr), False),
                                          'version': 3, 'strides': None}
 
 
@@ -167,7 +167,10 @@ class PeerExchange:
     rank's stack.  Two stacks alternate so that step s+1 may write while a slower rank still fuses step s.
     """
 
-    def __init__(self, engine, local_stack, view_counts, group=None, halo=1, buffers=2):
+    def __init__(self, engine, local_stack, view_counts, group=None, halo=1, buffers=2, sparse=True):
+        """sparse=True (default): stage B also maintains the owners' occupancy bitmaps and does not send all-empty
+        tiles; the owner fuses with vs_fuse_views_sparse ("skip all-NaN row-bands via an occupancy
+        flag").  sparse=False: every tile is stored, the band stacks are dense."""
         from . import _native
         self._native = _native
         self.group = group
@@ -190,7 +193,12 @@ class PeerExchange:
         lib, check = _native.lib, _native.check
         ctx = engine.ctx.handle
         my_rows = self.h1 - self.h0
-        nbytes = max(self.v_total * my_rows * self.W * 4, 4)
+        self.sparse = bool(sparse)
+        self.occ_shape = engine.occupancy_shape(self.v_total)                 # full-grid tile indexing on every rank
+        stack_bytes = max(self.v_total * my_rows * self.W * 4, 4)
+        self._occ_offset = (stack_bytes + 255) // 256 * 256                   # bitmap behind the stack, same allocation
+        occ_bytes = int(np.prod(self.occ_shape)) * 4
+        nbytes = self._occ_offset + occ_bytes
         # Set-up failures must be seen by every rank (a rank that raised alone would leave the others in a collective):
         # each phase ends with an exchange of success flags.
         self._own, self._opened, self._ptrs, handles, err = [], [], [], [], None
@@ -232,8 +240,15 @@ class PeerExchange:
             raise _native.VisSatError('PeerExchange: mapping peer memory failed on some rank: {}'.format(err))
         self.band_stacks = [torch.as_tensor(_DeviceArray(p, (self.v_total, my_rows, self.W)), device=local_stack.device)
                             for p in self._own]
+        self.occs = [torch.as_tensor(_DeviceArray(p + self._occ_offset, self.occ_shape, typestr='<i4'),
+                                     device=local_stack.device) for p in self._own]
+        for o in self.occs:
+            o.zero_()
+        torch.cuda.synchronize(local_stack.device)
+        dist.barrier(group=group)              # every bitmap is zero before any peer sets a bit
         self._flag = torch.zeros(1, dtype=torch.int32, device=local_stack.device)
         self._cur = -1
+        self.keep_last_occ = False     # diagnostics (check_band_stack)
 
     def _release(self):
         lib, ctx = self._native.lib, self.engine.ctx.handle
@@ -246,21 +261,61 @@ class PeerExchange:
 
     def begin_step(self):
         self._cur = (self._cur + 1) % self.n_buffers
+        self._barrier_done = False
         if self.local.shape[0] == 0:           # a rank without views launches nothing; it still takes part in finish()
             return
         ex = self._native.vs_exchange()
         ex.n_ranks, ex.rank, ex.halo = self.world, self.rank, self.halo
         ex.view0, ex.n_views_total = self.view0, self.v_total
         ex.local_stack = self.local.data_ptr()
+        ex.occ_words = self.occ_shape[2] if self.sparse else 0
         for r in range(self.world):
             ex.band_stack[r] = self._ptrs[self._cur][r]
+            ex.occ[r] = self._ptrs[self._cur][r] + self._occ_offset if self.sparse else None
         self.engine.set_exchange(ex)
+
+    def finish_barrier_only(self):
+        """The stream-ordered barrier of the step ("every rank's stage-B kernels, hence their peer stores, are complete")."""
+        if not getattr(self, '_barrier_done', False):
+            self.engine.set_exchange(None)
+            dist.all_reduce(self._flag, group=self.group)
+            self._barrier_done = True
 
     def finish(self):
         """Barrier on the current stream, then this rank's (V_total, rows + halo, W) stack of the step."""
-        self.engine.set_exchange(None)
-        dist.all_reduce(self._flag, group=self.group)
+        self.finish_barrier_only()
         return self.band_stacks[self._cur], self.bands[self.rank], (self.h0, self.h1)
+
+    def fuse_band(self, count_nan=True, out=None, after_barrier=False):
+        """finish() + stage C on this rank's rows: (fused band (rows, W), (r0, r1)).  In sparse mode only the marked
+        (tile, view) pairs of the stack are read, and the bitmap is cleared for the step after next."""
+        eng = self.engine
+        band_stack, (r0, r1), (h0, h1) = self.finish()
+        if r1 == r0:
+            return torch.empty((0, self.W), dtype=torch.float32, device=self.local.device), (r0, r1)
+        if not hasattr(self, '_mean_buf'):
+            self._mean_buf = torch.empty((h1 - h0, self.W), dtype=torch.float32, device=self.local.device)
+        occ = self.occs[self._cur] if self.sparse else None
+        mean = eng.fuse(band_stack, out=self._mean_buf, occ=occ, row0=h0)
+        if occ is not None:
+            if self.keep_last_occ:
+                self._last_occ = occ.clone()
+            occ.zero_()      # before this rank reaches the next barrier, i.e. before any peer writes this buffer again
+        out = eng.median3x3(mean, out=out, row_begin=r0, row_end=r1, in_row0=h0, h_total=self.n_rows, count_nan=count_nan)
+        return out, (r0, r1)
+
+    def check_band_stack(self, want_dense):
+        """Diagnostics: the current stack, read under the sparse convention, equals the dense stack `want_dense`.
+        Call between finish() and the next begin_step(); in sparse mode BEFORE fuse_band() clears the bitmap -- so
+        fuse_band() keeps a copy of the last bitmap for this check."""
+        stack = self.band_stacks[self._cur]
+        if self.sparse:
+            occ = getattr(self, '_last_occ', None)
+            if occ is None:
+                return False
+            stack = self.engine.densify(stack, occ, row0=self.h0)
+        return stack.shape == want_dense.shape and torch.equal(torch.nan_to_num(stack, nan=-1e9),
+                                                               torch.nan_to_num(want_dense, nan=-1e9))
 
     def close(self):
         lib, ctx = self._native.lib, self.engine.ctx.handle
@@ -268,6 +323,8 @@ class PeerExchange:
         self.engine.set_exchange(None)
         dist.barrier(group=self.group)         # nobody is still writing into a stack that is about to be unmapped
         self.band_stacks = []
+        self.occs = []
+        self._last_occ = None
         for p in self._opened:
             lib.vs_peer_close(ctx, C.c_void_p(p))
         self._opened = []
@@ -277,12 +334,12 @@ class PeerExchange:
         self._own = []
 
 
-def make_exchange(engine, local_stack, view_counts, group=None, prefer='peer'):
+def make_exchange(engine, local_stack, view_counts, group=None, prefer='peer', sparse=True):
     """PeerExchange when every rank can set it up (its constructor fails on all ranks or on none), else WaveExchanger.
     Returns (exchanger, kind)."""
     if prefer == 'peer' and local_stack.is_cuda:
         try:
-            return PeerExchange(engine, local_stack, view_counts, group=group), 'peer-store'
+            return PeerExchange(engine, local_stack, view_counts, group=group, sparse=sparse), 'peer-store'
         except Exception as e:      # e.g. no peer access between the devices, IPC not permitted in this container
             if dist.get_rank(group) == 0:
                 print('PeerExchange unavailable ({}); using NCCL waves'.format(e), flush=True)

@@ -137,7 +137,7 @@ class DsmEngine:
                                   _ptr(self.keygrid), _ptr(out), stack.stride(0), self.simd_lanes,
                                   _ptr(count_nan), _ptr(stats), _stream(self.device)), 'vs_views_to_dsm')
 
-    def capture_step(self, depths, mats, stack, fuse=True):
+    def capture_step(self, depths, mats, stack, fuse=True, occ=None):
         """Stages A-C for a fixed set of device buffers as ONE CUDA graph (102 kernel launches + 50 memsets for 50 views): replaying
         it costs one launch call on the host and removes the per-launch gaps on the device.  The step is run eagerly
         once first (every lazy allocation inside the library happens there), then captured; the internal streams of
@@ -146,10 +146,13 @@ class DsmEngine:
         self.set_timing(False)
 
         def body():
+            if occ is not None:
+                occ.zero_()
+                self.set_occupancy(occ, stack, 0)
             self.views_to_dsm(depths, mats, stack)
             if not fuse:
                 return None
-            return self.median3x3(self.fuse(stack), count_nan=True)
+            return self.median3x3(self.fuse(stack, occ=occ), count_nan=True)
 
         body()
         torch.cuda.synchronize(self.device)
@@ -158,6 +161,24 @@ class DsmEngine:
         with torch.cuda.graph(graph):
             fused = body()
         return StepGraph(graph, fused, self.launch_count() - n0)
+
+    # ---- occupancy bitmap (sparse coverage: large AOIs) -----------------------------------------------------------
+    def occupancy_shape(self, n_views):
+        """(tile rows, tile columns, words) of the bitmap for n_views views (vs_set_occupancy layout)."""
+        return (-(-self.n_size // _native.VS_TILE_H), -(-self.e_size // _native.VS_TILE_W), -(-int(n_views) // 32))
+
+    def alloc_occupancy(self, n_views):
+        return torch.zeros(self.occupancy_shape(n_views), dtype=torch.int32, device=self.device)
+
+    def set_occupancy(self, occ, stack=None, view0=0):
+        """Make stage B (views_to_dsm) record in `occ` which (tile, view) pairs of `stack` hold data; plane i of `stack`
+        is global view view0 + i.  occ=None switches it off.  The caller zeroes `occ` before each pass over the views."""
+        if occ is None:
+            check(lib.vs_set_occupancy(self.ctx.handle, C.c_void_p(0), 0, C.c_void_p(0), 0), 'vs_set_occupancy')
+            return
+        assert occ.is_cuda and occ.dtype == torch.int32 and occ.is_contiguous() and occ.dim() == 3
+        assert tuple(occ.shape[:2]) == self.occupancy_shape(1)[:2]
+        check(lib.vs_set_occupancy(self.ctx.handle, _ptr(occ), occ.shape[2], _ptr(stack), int(view0)), 'vs_set_occupancy')
 
     def set_exchange(self, ex):
         """Enable (a _native.vs_exchange) or disable (None) the peer stores of stage B (distributed.PeerExchange)."""
@@ -186,16 +207,35 @@ class DsmEngine:
         return int(self._nan_count.cpu().item())
 
     # ---- stage C ------------------------------------------------------------------------------------------
-    def fuse(self, views, out=None):
-        """aggregate_2p5d.py:65-78 on a (V, rows, W) float32 stack of per-view DSMs (device)."""
+    def fuse(self, views, out=None, occ=None, row0=0):
+        """aggregate_2p5d.py:65-78 on a (V, rows, W) float32 stack of per-view DSMs (device).
+        occ: optional occupancy bitmap filled by stage B (set_occupancy / the sparse peer exchange): only the marked
+        (tile, view) pairs are read, the rest count as NaN; `views` then holds grid rows [row0, row0 + rows)."""
         assert views.is_cuda and views.dtype == torch.float32 and views.dim() == 3
         V, rows, W = views.shape
         assert views.stride(2) == 1 and views.stride(1) == W, 'planes must be row-major contiguous'
         if out is None:
             out = torch.empty((rows, W), dtype=torch.float32, device=self.device)
+        if occ is not None:
+            assert occ.is_cuda and occ.dtype == torch.int32 and occ.is_contiguous() and occ.dim() == 3
+            assert occ.shape[1] == -(-W // _native.VS_TILE_W) and occ.shape[0] * _native.VS_TILE_H >= row0 + rows
+            check(lib.vs_fuse_views_sparse(self.ctx.handle, _ptr(views), views.stride(0), V, rows, W, int(row0), _ptr(occ),
+                                           occ.shape[2], _ptr(out), _stream(self.device)), 'vs_fuse_views_sparse')
+            return out
         check(lib.vs_fuse_views(self.ctx.handle, _ptr(views), views.stride(0), V, rows, W, _ptr(out),
                                 _stream(self.device)), 'vs_fuse_views')
         return out
+
+    def densify(self, views, occ, row0=0):
+        """Copy of `views` with every (tile, view) pair the bitmap does not mark set to NaN -- what the stack means under
+        the sparse convention (diagnostics / tests; plain torch indexing, not a hot path)."""
+        V, rows, W = views.shape
+        g = torch.arange(V, device=views.device)
+        bits = (occ[:, :, (g // 32)] >> (g % 32).to(torch.int32)) & 1                       # (Ty, Tx, V)
+        m = bits.permute(2, 0, 1).bool()
+        m = m.repeat_interleave(_native.VS_TILE_H, dim=1)[:, row0:row0 + rows]
+        m = m.repeat_interleave(_native.VS_TILE_W, dim=2)[:, :, :W]
+        return torch.where(m, views, torch.full_like(views, float('nan')))
 
     def median3x3(self, img, out=None, row_begin=0, row_end=None, in_row0=0, h_total=None, count_nan=False):
         """aggregate_2p5d.py:81: cv2.medianBlur(float32, 3) of rows [row_begin, row_end) of an h_total-row image

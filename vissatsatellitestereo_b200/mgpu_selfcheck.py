@@ -56,6 +56,7 @@ def check_case(name, grid_w, grid_h, n_views, base, dev, rank, world, log=None):
     ok_peer, peer_state = True, 'OK'
     try:
         px = D.PeerExchange(eng, torch.empty_like(local), counts)      # fails on every rank or on none
+        px.keep_last_occ = True
     except Exception as e:
         px, peer_state = None, 'UNAVAILABLE ({})'.format(e)
     for step in range(3 if px is not None else 0):
