@@ -374,3 +374,44 @@ def test_tma_pipeline_variant_is_bit_identical(golden, eng_mod, lanes, monkeypat
         band = t[r0 - 1:r1 + 1].contiguous()
         got = tma.median3x3(band, row_begin=r0, row_end=r1, in_row0=r0 - 1, h_total=shape[0]).cpu().numpy()
         assert _eq(got, want[r0:r1])
+
+
+def test_key_space_stage_b_bit_identical_to_round1_kernel(eng_mod, lanes, monkeypatch):
+    """finalize_keys.cu (default: hole fill + 3x3 median computed on the order-preserving keys) against the round-1
+    float-space kernel (VISSAT_K2_LEGACY=1, itself pinned to cv2 / the reference goldens) on random key grids: all hole
+    densities, NaN regions wider than the fill, odd row pitch, edge tiles, 1-row / 1-column grids."""
+    from vissatsatellitestereo_b200 import synthetic as S
+    import ctypes as C
+    from vissatsatellitestereo_b200._native import lib, check
+    cfg = S.scaled(S.CONFIGS['C1'], views=1, depth=64, grid=32)
+    aoi = S.make_aoi(cfg, geodesy)
+    new = eng_mod.DsmEngine(aoi, cfg.res, cfg.res, simd_lanes=lanes)
+    monkeypatch.setenv('VISSAT_K2_LEGACY', '1')
+    old = eng_mod.DsmEngine(aoi, cfg.res, cfg.res, simd_lanes=lanes)
+    monkeypatch.delenv('VISSAT_K2_LEGACY')
+    rng = np.random.default_rng(5)
+
+    def run(e, keys, W, H):
+        out = torch.empty((H, W), dtype=torch.float32, device='cuda')
+        cnt = torch.zeros(1, dtype=torch.int64, device='cuda')
+        check(lib.vs_grid_finalize(e.ctx.handle, C.c_void_p(keys.data_ptr()), W, H, C.c_void_p(out.data_ptr()), lanes,
+                                   C.c_void_p(cnt.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return out.cpu().numpy(), int(cnt.item())
+
+    shapes = [(1, 1), (1, 37), (41, 1), (2, 2), (5, 17), (36, 72), (64, 128), (97, 131), (200, 260), (257, 516), (300, 64)]
+    for (H, W) in shapes:
+        for p_hole in (0.0, 0.1, 0.4, 0.8, 0.97, 1.0):
+            alt = (30 + 20 * rng.normal(size=(H, W))).astype(np.float32)
+            alt[rng.random((H, W)) < 0.1] = np.round(alt[rng.random((H, W)) < 0.1].mean())         # ties
+            b = alt.view(np.uint32)
+            keys = np.where(b >> 31 != 0, ~b, b | np.uint32(0x80000000)).astype(np.uint32)
+            keys[rng.random((H, W)) < p_hole] = 0
+            if H > 20 and W > 20:
+                keys[H // 3:H // 3 + 9, W // 4:W // 4 + 11] = 0                                     # NaNs survive the fill
+            kt = torch.from_numpy(keys.view(np.int32)).cuda()
+            a, na = run(new, kt, W, H)
+            o, no = run(old, kt, W, H)
+            assert np.array_equal(a, o, equal_nan=True), (H, W, p_hole)
+            assert na == no == int(np.isnan(a).sum())
+    new.close()
+    old.close()

@@ -162,6 +162,8 @@ int vs_ctx_create(int device, vs_ctx** out) {
         // shared-memory pass and the kernel is ALU-bound, not load-latency-bound), so it is opt-in.
         const char* e = getenv("VISSAT_TMA");
         ctx->no_tma = !(e != nullptr && e[0] == '1');
+        const char* l = getenv("VISSAT_K2_LEGACY");
+        ctx->k2_legacy = l != nullptr && l[0] == '1';
     }
     ctx->ev_used = 0;
     *out = ctx;

@@ -12,6 +12,8 @@
 //       * a tile without any NaN left skips every NaN test; otherwise each window with a NaN goes through the
 //         exact emulation of OpenCV's 19-exchange network (SIMD / scalar column semantics).
 // K4  k_median3x3            aggregate_2p5d.py:81 on a row band (halo rows supplied by the caller); same blur.
+#include <stdlib.h>
+
 #include "finalize_common.cuh"
 
 using namespace vsfin;
@@ -314,10 +316,22 @@ k_median3x3(const float* __restrict__ in, int in_row0, int H, int W, int row_beg
 
 }  // namespace
 
+// key-space kernels (finalize_keys.cu): the default float32-key path.  VISSAT_K2_LEGACY=1 selects the round-1 kernels
+// of this file (k_grid_finalize<uint32_t, .>), kept for A/B measurements; both are bit-identical.
+int vs_launch_finalize_keys(vs_ctx* ctx, const uint32_t* keygrid, int xsize, int ysize, float* dsm_out, int simd_cols,
+                            unsigned long long* nan_count, cudaStream_t stream);
+int vs_launch_finalize_keys_occ(vs_ctx* ctx, const uint32_t* keygrid, int xsize, int ysize, float* dsm_out, int simd_cols,
+                                unsigned long long* nan_count, const VsOccPlan& plan, cudaStream_t stream);
+int vs_launch_finalize_keys_peer(vs_ctx* ctx, const uint32_t* keygrid, int xsize, int ysize, float* dsm_out, int simd_cols,
+                                 unsigned long long* nan_count, const VsPeerPlan& plan, cudaStream_t stream);
+
 // Stage B of one view with the peer stores of the multi-GPU exchange (called by vs_views_to_dsm, pipeline.cu).
 int vs_grid_finalize_peer(vs_ctx* ctx, const uint32_t* keygrid, int xsize, int ysize, float* dsm_out, int simd_lanes,
                           uint64_t* nan_count, const VsPeerPlan& plan, cudaStream_t stream) {
     if (nan_count) VS_CUDA(cudaMemsetAsync(nan_count, 0, sizeof(uint64_t), stream));
+    if (!ctx->k2_legacy)
+        return vs_launch_finalize_keys_peer(ctx, keygrid, xsize, ysize, dsm_out, simd_cols_for(xsize, simd_lanes),
+                                            reinterpret_cast<unsigned long long*>(nan_count), plan, stream);
     PeerSink sink;
     sink.p = plan;
     dim3 grid((xsize + TW - 1) / TW, (ysize + TH - 1) / TH);
@@ -333,6 +347,9 @@ int vs_grid_finalize_peer(vs_ctx* ctx, const uint32_t* keygrid, int xsize, int y
 int vs_grid_finalize_occ(vs_ctx* ctx, const uint32_t* keygrid, int xsize, int ysize, float* dsm_out, int simd_lanes,
                          uint64_t* nan_count, const VsOccPlan& plan, cudaStream_t stream) {
     if (nan_count) VS_CUDA(cudaMemsetAsync(nan_count, 0, sizeof(uint64_t), stream));
+    if (!ctx->k2_legacy)
+        return vs_launch_finalize_keys_occ(ctx, keygrid, xsize, ysize, dsm_out, simd_cols_for(xsize, simd_lanes),
+                                           reinterpret_cast<unsigned long long*>(nan_count), plan, stream);
     OccSink sink;
     sink.o = plan;
     dim3 grid((xsize + TW - 1) / TW, (ysize + TH - 1) / TH);
@@ -366,6 +383,9 @@ int vs_grid_finalize(vs_ctx* ctx, const uint32_t* keygrid, int32_t xsize, int32_
         if (r < 0) return VS_ERR_CUDA;
         if (r > 0) return VS_OK;
     }
+    if (!ctx->k2_legacy)
+        return vs_launch_finalize_keys(ctx, keygrid, xsize, ysize, dsm_out, simd_cols_for(xsize, simd_lanes),
+                                       reinterpret_cast<unsigned long long*>(nan_count), stream);
     dim3 grid((xsize + TW - 1) / TW, (ysize + TH - 1) / TH);
     k_grid_finalize<uint32_t, NoSink><<<grid, kThreads, 0, stream>>>(keygrid, xsize, ysize, nullptr, dsm_out,
                                                                     simd_cols_for(xsize, simd_lanes),

@@ -17,6 +17,9 @@
 // V > 128:  k_fuse_large  -- 4, 8 or 32 threads per cell, sorted runs in shared memory, bitwise bisection.
 #include <math_constants.h>
 
+#include <stdlib.h>
+#include <string.h>
+
 #include <algorithm>
 
 #include "sortnets_gen.cuh"
@@ -521,6 +524,7 @@ constexpr int kSparseBins = 19;
 __constant__ int c_bin_cap[kSparseBins] = {8, 16, 24, 32, 40, 48, 56, 64, 80, 96, 112, 128, 160, 208, 256, 416, 512, 1024, 2048};
 static const int h_bin_cap[kSparseBins] = {8, 16, 24, 32, 40, 48, 56, 64, 80, 96, 112, 128, 160, 208, 256, 416, 512, 1024, 2048};
 constexpr int kMaxOccWords = 64;   // 2048 views
+constexpr int kMaxLeaves = 32;     // 2048 views / 64-element minimum leaf
 
 struct SparseGeom {
     const float* views;
@@ -532,7 +536,40 @@ struct SparseGeom {
     const int* bin_count;      // [kSparseBins]
     const int* bin_list;       // [kSparseBins][n_units]
     float* out;
+    // numpy's pairwise-sum tree over the view axis [0, V), leaves left to right (host-built, make_sum_tree):
+    // leaf l covers views [leaf_off[l], leaf_off[l] + leaf_n[l]); after it, leaf_pops[l] partial sums are folded
+    int n_leaves;
+    short leaf_off[kMaxLeaves], leaf_n[kMaxLeaves];
+    signed char leaf_pops[kMaxLeaves];
 };
+
+// Leaves of numpy's float32 pairwise add.reduce over n elements: blocks of <= 128 elements, split at
+// n/2 rounded down to a multiple of 8.  pops[l] = how many finished left siblings are added after leaf l.
+static void make_sum_tree(int V, SparseGeom& g) {
+    struct Seg { int off, n, lvl; };
+    Seg todo[64];
+    int tp = 0, nl = 0;
+    int lvl_stack[32], sp = 0;
+    todo[tp++] = {0, V, 0};
+    while (tp > 0) {
+        const Seg sgm = todo[--tp];
+        if (sgm.n > 128) {
+            int n2 = sgm.n >> 1;
+            n2 -= n2 & 7;
+            todo[tp++] = {sgm.off + n2, sgm.n - n2, sgm.lvl + 1};
+            todo[tp++] = {sgm.off, n2, sgm.lvl + 1};
+            continue;
+        }
+        int pops = 0, l = sgm.lvl;
+        while (sp > 0 && lvl_stack[sp - 1] == l) { --sp; --l; ++pops; }
+        lvl_stack[sp++] = l;
+        g.leaf_off[nl] = (short)sgm.off;
+        g.leaf_n[nl] = (short)sgm.n;
+        g.leaf_pops[nl] = (signed char)pops;
+        ++nl;
+    }
+    g.n_leaves = nl;
+}
 
 __global__ void k_fuse_plan(const uint32_t* __restrict__ occ, int occ_words, int tiles_x, int ty_first, int n_units,
                             int* __restrict__ bin_count, int* __restrict__ bin_list) {
@@ -581,83 +618,52 @@ __device__ __forceinline__ int build_view_list(const uint32_t* __restrict__ occ_
     return s_n;
 }
 
-// numpy's pairwise sum over the original view axis [0, V), one thread per cell, absent views skipped
-template <typename Present>
-__device__ __forceinline__ float leaf_sum_1t(const KeepFn& y, const Present& present, int off, int n, int& cnt) {
-    if (n < 8) {
-        float res = 0.0f;
-        for (int i = 0; i < n; ++i)
-            if (present(off + i)) {
-                res = __fadd_rn(res, y(off + i));
-                cnt += y.kept(off + i);
+// numpy's pairwise sum over the ORIGINAL view axis [0, V), one thread per cell, driven by the tile's ascending view list:
+// absent views would add +0, so only the listed ones are visited, each into the accumulator numpy would use
+// (r[(v - leaf offset) % 8] inside the leaf's full blocks of 8, the tail sequentially), leaves folded as the recursion
+// does.  The list is CTA-uniform, so the accumulator switch is a uniform branch.
+__device__ __forceinline__ float sparse_sum_1t(const SparseGeom& g, const int* __restrict__ s_list, int n,
+                                               const float* __restrict__ cellp, float med, float mad) {
+    const KeepFn y{cellp, g.plane_stride, med, mad};
+    int e = 0, cnt = 0, sp = 0;
+    float st[8];
+    for (int L = 0; L < g.n_leaves; ++L) {
+        const int off = g.leaf_off[L], nl = g.leaf_n[L];
+        const int full_end = off + (nl < 8 ? 0 : nl - (nl & 7)), end = off + nl;
+        float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f, r4 = 0.f, r5 = 0.f, r6 = 0.f, r7 = 0.f;
+        while (e < n) {
+            const int v = s_list[e];
+            if (v >= full_end) break;
+            const float t = __ldg(y.p + (int64_t)v * y.stride);
+            const bool keep = (t == t) && !(fabsf(__fsub_rn(t, med)) > mad);
+            const float x = keep ? t : 0.0f;
+            cnt += keep;
+            switch ((v - off) & 7) {      // uniform across the CTA
+                case 0: r0 = __fadd_rn(r0, x); break;
+                case 1: r1 = __fadd_rn(r1, x); break;
+                case 2: r2 = __fadd_rn(r2, x); break;
+                case 3: r3 = __fadd_rn(r3, x); break;
+                case 4: r4 = __fadd_rn(r4, x); break;
+                case 5: r5 = __fadd_rn(r5, x); break;
+                case 6: r6 = __fadd_rn(r6, x); break;
+                default: r7 = __fadd_rn(r7, x); break;
             }
-        return res;
-    }
-    float r[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        r[j] = 0.0f;
-        if (present(off + j)) {
-            r[j] = y(off + j);
-            cnt += y.kept(off + j);
+            ++e;
         }
-    }
-    const int nfull = n - (n & 7);
-    for (int i = 8; i < nfull; i += 8) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-            if (present(off + i + j)) {
-                r[j] = __fadd_rn(r[j], y(off + i + j));
-                cnt += y.kept(off + i + j);
-            }
-    }
-    float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
-                          __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
-    for (int i = nfull; i < n; ++i)
-        if (present(off + i)) {
-            res = __fadd_rn(res, y(off + i));
-            cnt += y.kept(off + i);
+        float res = __fadd_rn(__fadd_rn(__fadd_rn(r0, r1), __fadd_rn(r2, r3)), __fadd_rn(__fadd_rn(r4, r5), __fadd_rn(r6, r7)));
+        while (e < n) {
+            const int v = s_list[e];
+            if (v >= end) break;
+            const float t = __ldg(y.p + (int64_t)v * y.stride);
+            const bool keep = (t == t) && !(fabsf(__fsub_rn(t, med)) > mad);
+            res = __fadd_rn(res, keep ? t : 0.0f);
+            cnt += keep;
+            ++e;
         }
-    return res;
-}
-
-template <typename Present>
-__device__ __forceinline__ float sum_survivors_1t(const KeepFn& y, const Present& present, int V) {
-    int cnt = 0;
-    float total;
-    if (V <= 128) {
-        total = leaf_sum_1t(y, present, 0, V, cnt);
-    } else {   // numpy's recursion tree, walked left to right with an explicit stack (as sum_survivors above)
-        float stack_val[12];
-        int stack_lvl[12];
-        int sp = 0;
-        int seg_off[12], seg_n[12], seg_lvl[12];
-        int tp = 1;
-        seg_off[0] = 0; seg_n[0] = V; seg_lvl[0] = 0;
-        while (tp > 0) {
-            --tp;
-            const int off = seg_off[tp], n = seg_n[tp], lvl = seg_lvl[tp];
-            if (n > 128) {
-                int n2 = n >> 1;
-                n2 -= n2 & 7;
-                seg_off[tp] = off + n2; seg_n[tp] = n - n2; seg_lvl[tp] = lvl + 1; ++tp;
-                seg_off[tp] = off; seg_n[tp] = n2; seg_lvl[tp] = lvl + 1; ++tp;
-                continue;
-            }
-            float val = leaf_sum_1t(y, present, off, n, cnt);
-            int l = lvl;
-            while (sp > 0 && stack_lvl[sp - 1] == l) {
-                val = __fadd_rn(stack_val[sp - 1], val);
-                --sp;
-                --l;
-            }
-            stack_val[sp] = val;
-            stack_lvl[sp] = l;
-            ++sp;
-        }
-        total = stack_val[0];
+        for (int q = 0; q < g.leaf_pops[L]; ++q) res = __fadd_rn(st[--sp], res);
+        st[sp++] = res;
     }
-    return __fdiv_rn(total, (float)cnt);
+    return __fdiv_rn(st[0], (float)cnt);
 }
 
 // rows of unit u (a tile clipped to the planes' rows), split into 4 slabs of 8 tile rows
@@ -667,7 +673,7 @@ __device__ __forceinline__ void unit_geometry(const SparseGeom& g, int u, int& t
 }
 
 template <int NV>
-__global__ void __launch_bounds__(kBlockSmall, (NV > 64 && NV <= 112) ? 4 : 1)
+__global__ void __launch_bounds__(kBlockSmall, NV <= 32 ? 6 : NV <= 64 ? 5 : NV <= 112 ? 4 : 2)
 k_fuse_sparse_regs(const __grid_constant__ SparseGeom g, int bin) {
     __shared__ uint32_t s_bits[kMaxOccWords];
     __shared__ int s_list[NV];
@@ -680,7 +686,6 @@ k_fuse_sparse_regs(const __grid_constant__ SparseGeom g, int bin) {
         const int n = build_view_list(g.occ + ((size_t)ty * g.tiles_x + tx) * g.occ_words, g.occ_words, s_bits, s_list, NV);
         const int gy0 = max(ty * VS_TILE_H + (item & 3) * 8, g.row0);
         const int gy1 = min(min(ty * VS_TILE_H + (item & 3) * 8 + 8, g.row0 + g.rows), (ty + 1) * VS_TILE_H);
-        const BitsPresent present{s_bits};
         for (int c = threadIdx.x; c < VS_TILE_W * (gy1 - gy0); c += kBlockSmall) {
             const int gy = gy0 + (c >> 6), gx = tx * VS_TILE_W + (c & 63);
             if (gx >= g.W) continue;
@@ -705,8 +710,7 @@ k_fuse_sparse_regs(const __grid_constant__ SparseGeom g, int bin) {
             for (int i = 0; i < NV; ++i) s[i] = fabsf(__fsub_rn(s[i], med));
             bitonic_merge_regs<NV>(s);
             const float mad = middle_of_sorted<NV>(s, k);
-            const KeepFn y{g.views + cell, g.plane_stride, med, mad};
-            g.out[cell] = sum_survivors_1t(y, present, g.V);
+            g.out[cell] = sparse_sum_1t(g, s_list, n, g.views + cell, med, mad);
         }
     }
 }
@@ -794,6 +798,179 @@ k_fuse_sparse_large(const __grid_constant__ SparseGeom g, int bin, int VS) {
             if (lane == 0) g.out[cell] = mean;
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// 129..208 views per cell: TWO threads per cell (adjacent lanes), each sorting up to NVL values in registers with the
+// same networks as the one-thread path; the order statistics of the union come from one cross step -- thread A keeps
+// min(a[i], b[NVL-1-i]) (the NVL smallest of the union, a bitonic sequence), thread B the max (the NVL largest) -- and
+// one bitonic merge per thread.  |x - med| is bitonic over A's sorted half and already ascending over B's, so the MAD
+// costs one more merge + cross step + merge.  No shared memory, no bisection.  (The multi-lane shared-memory kernel
+// above remains for more than 208 views.)
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kPairThreads = 128;   // 64 cells per CTA pass
+
+// Bitonic merge into DESCENDING order of a "mountain" (rises, then falls) held in N registers; N is padded to a power
+// of two with virtual -inf wires at the end, which continue the falling part and never move.
+template <int N>
+__device__ __forceinline__ void bitonic_merge_regs_desc(float (&a)[N]) {
+    constexpr int N2 = N <= 8 ? 8 : N <= 16 ? 16 : N <= 32 ? 32 : N <= 64 ? 64 : 128;
+#pragma unroll
+    for (int j = N2 / 2; j > 0; j >>= 1) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const int l = i ^ j;
+            if (l > i && l < N) {
+                const float hi = fmaxf(a[i], a[l]);
+                const float lo = fminf(a[i], a[l]);
+                a[i] = hi;
+                a[l] = lo;
+            }
+        }
+    }
+}
+
+template <int NVL>
+__device__ __forceinline__ float pick_reg(const float (&s)[NVL], int idx) {
+    float r = s[0];
+#pragma unroll
+    for (int i = 1; i < NVL; ++i) r = (i == idx) ? s[i] : r;
+    return r;
+}
+
+// One cell, computed by the two lanes of a pair (lane A even, lane B odd); med / mad are returned on both lanes.
+// slot(i) -> plane index of the i-th listed view (i < n), cellp = views + cell.
+//
+// A takes the even list slots, B the odd ones, and B works on NEGATED values: after both sorted ascending,
+// B's element i is -(its (NVL-1-i)-th smallest), so the classic split "A keeps min(a[i], b[NVL-1-i]), B keeps the max"
+// becomes the SAME instruction on both lanes, t[i] = min(own[i], -partner[i]), with no index reversal; both results are
+// mountains, sorted by the same descending merge.  A then holds the NVL smallest values of the union in descending
+// order (rank r at index NVL-1-r), B minus the NVL largest (the smallest of them at index 0).
+template <int NVL, typename SlotFn>
+__device__ __forceinline__ void fuse_cell_pair(const SlotFn& slot, int n, const float* __restrict__ cellp, int64_t stride,
+                                               bool is_b, unsigned pm, float& med_out, float& mad_out, int& k_out) {
+    const int lane_a = (threadIdx.x & 31) & ~1;
+    const uint32_t sign = is_b ? 0x80000000u : 0u;
+    float s[NVL];
+    int k_lane = 0;
+#pragma unroll
+    for (int i = 0; i < NVL; ++i) {
+        const int sl = 2 * i + (is_b ? 1 : 0);
+        float t = CUDART_NAN_F;
+        if (sl < n) t = __ldg(cellp + (int64_t)slot(sl) * stride);
+        const bool ok = (t == t);
+        k_lane += ok;
+        s[i] = __uint_as_float(__float_as_uint(ok ? t : CUDART_INF_F) ^ sign);     // B: negated
+    }
+    const int k = k_lane + __shfl_xor_sync(pm, k_lane, 1);
+    k_out = k;
+    if (k <= 2) return;                      // both lanes of the pair agree (aggregate_2p5d.py:69-71)
+    SortNet<NVL>::sort(s);
+    float t2[NVL];
+#pragma unroll
+    for (int i = 0; i < NVL; ++i) t2[i] = fminf(s[i], -__shfl_xor_sync(pm, s[i], 1));
+    bitonic_merge_regs_desc<NVL>(t2);
+    const int ilo = (k - 1) >> 1, ihi = k >> 1;        // ranks in the union; ilo <= NVL - 1 because k <= 2 NVL
+    float up0 = -__shfl_xor_sync(pm, t2[0], 1);        // on A: the smallest of the upper half
+    float lo = pick_reg<NVL>(t2, NVL - 1 - ilo);
+    float hi = (ihi < NVL) ? pick_reg<NVL>(t2, NVL - 1 - ihi) : up0;
+    float med = __shfl_sync(pm, __fdiv_rn(__fadd_rn(lo, hi), 2.0f), lane_a);
+    // |x - med|: on A a valley over the descending half (falls to the median, rises below it; +inf pads in front),
+    // on B (true values -t2[i] >= med, ascending in i) already ascending.  Same instructions on both lanes.
+    const float smed = __uint_as_float(__float_as_uint(med) ^ sign);
+#pragma unroll
+    for (int i = 0; i < NVL; ++i) s[i] = fabsf(__fsub_rn(t2[i], smed));
+    bitonic_merge_regs<NVL>(s);                          // ascending (+inf pads); a no-op on B's ascending run
+    // second split: A keeps its ascending run, B turns its run into minus the reversed run
+#pragma unroll
+    for (int i = 0; i < NVL; ++i) t2[i] = is_b ? -s[NVL - 1 - i] : s[i];
+#pragma unroll
+    for (int i = 0; i < NVL; ++i) s[i] = fminf(t2[i], -__shfl_xor_sync(pm, t2[i], 1));
+    bitonic_merge_regs_desc<NVL>(s);
+    up0 = -__shfl_xor_sync(pm, s[0], 1);
+    lo = pick_reg<NVL>(s, NVL - 1 - ilo);
+    hi = (ihi < NVL) ? pick_reg<NVL>(s, NVL - 1 - ihi) : up0;
+    mad_out = __shfl_sync(pm, __fdiv_rn(__fadd_rn(lo, hi), 2.0f), lane_a);
+    med_out = med;
+}
+
+struct ListSlot {
+    const int* list;
+    __device__ __forceinline__ int operator()(int i) const { return list[i]; }
+};
+struct IdentitySlot {
+    __device__ __forceinline__ int operator()(int i) const { return i; }
+};
+
+template <int NVL>
+__global__ void __launch_bounds__(kPairThreads, 4)
+k_fuse_sparse_pair(const __grid_constant__ SparseGeom g, int bin) {
+    __shared__ uint32_t s_bits[kMaxOccWords];
+    __shared__ int s_list[2 * NVL];
+    const int n_items = g.bin_count[bin] * 4;
+    const bool is_b = threadIdx.x & 1;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int u = g.bin_list[(size_t)bin * g.n_units + (item >> 2)];
+        int ty, tx;
+        unit_geometry(g, u, ty, tx);
+        __syncthreads();
+        const int n = build_view_list(g.occ + ((size_t)ty * g.tiles_x + tx) * g.occ_words, g.occ_words, s_bits, s_list, 2 * NVL);
+        const int gy0 = max(ty * VS_TILE_H + (item & 3) * 8, g.row0);
+        const int gy1 = min(min(ty * VS_TILE_H + (item & 3) * 8 + 8, g.row0 + g.rows), (ty + 1) * VS_TILE_H);
+        const ListSlot slot{s_list};
+        const unsigned pm = 3u << ((threadIdx.x & 31) & ~1);      // the two lanes of this cell
+        for (int row = gy0; row < gy1; ++row) {
+            const int gx = tx * VS_TILE_W + (threadIdx.x >> 1);
+            if (gx >= g.W) continue;                     // the pair leaves together
+            const int64_t cell = (int64_t)(row - g.row0) * g.W + gx;
+            float med = 0.f, mad = 0.f;
+            int k = 0;
+            fuse_cell_pair<NVL>(slot, n, g.views + cell, g.plane_stride, is_b, pm, med, mad, k);
+            if (is_b) continue;
+            g.out[cell] = (k <= 2) ? CUDART_NAN_F : sparse_sum_1t(g, s_list, n, g.views + cell, med, mad);
+        }
+    }
+}
+
+// dense stacks, 129..208 views: the same pair path with the identity list
+template <int NVL>
+__global__ void __launch_bounds__(kPairThreads, 4)
+k_fuse_pair(const __grid_constant__ SparseGeom g, int64_t n_cells) {
+    __shared__ int s_list[2 * NVL];
+    for (int i = threadIdx.x; i < 2 * NVL; i += kPairThreads) s_list[i] = i;
+    __syncthreads();
+    const bool is_b = threadIdx.x & 1;
+    const int64_t cell = blockIdx.x * (int64_t)(kPairThreads / 2) + (threadIdx.x >> 1);
+    if (cell >= n_cells) return;
+    float med = 0.f, mad = 0.f;
+    int k = 0;
+    fuse_cell_pair<NVL>(IdentitySlot(), g.V, g.views + cell, g.plane_stride, is_b, 3u << ((threadIdx.x & 31) & ~1), med, mad, k);
+    if (is_b) return;
+    g.out[cell] = (k <= 2) ? CUDART_NAN_F : sparse_sum_1t(g, s_list, g.V, g.views + cell, med, mad);
+}
+
+template <int NVL>
+int launch_sparse_pair(vs_ctx* ctx, const SparseGeom& g, int bin, cudaStream_t stream) {
+    const int blocks = std::min(g.n_units * 4, ctx->sm_count * 8);
+    k_fuse_sparse_pair<NVL><<<blocks, kPairThreads, 0, stream>>>(g, bin);
+    VS_CHECK_LAUNCH(ctx, "k_fuse_sparse_pair");
+    return VS_OK;
+}
+
+template <int NVL>
+int launch_pair(vs_ctx* ctx, const float* views, int64_t plane_stride, int V, int64_t n_cells, float* out,
+                cudaStream_t stream) {
+    SparseGeom g;
+    memset(&g, 0, sizeof(g));
+    g.views = views;
+    g.plane_stride = plane_stride;
+    g.V = V;
+    g.out = out;
+    make_sum_tree(V, g);
+    const int64_t blocks = (n_cells + kPairThreads / 2 - 1) / (kPairThreads / 2);
+    k_fuse_pair<NVL><<<(unsigned)blocks, kPairThreads, 0, stream>>>(g, n_cells);
+    VS_CHECK_LAUNCH(ctx, "k_fuse_pair");
+    return VS_OK;
 }
 
 template <int NV>
@@ -906,6 +1083,15 @@ extern "C" int vs_fuse_views(vs_ctx* ctx, const float* views, int64_t plane_stri
     if (V <= 112) return launch_medium<112>(ctx, views, plane_stride, V, n_cells, out_mean, stream);
     if (V <= 120) return launch_medium<120>(ctx, views, plane_stride, V, n_cells, out_mean, stream);
     if (V <= 128) return launch_medium<128>(ctx, views, plane_stride, V, n_cells, out_mean, stream);
+    // 129..208 views: two threads per cell, register networks + one cross step (k_fuse_pair); beyond: multi-lane runs in
+    // shared memory (k_fuse_large).  VISSAT_FUSE_PAIR=0 keeps the round-1 path for A/B measurements.
+    static const bool use_pair = []() { const char* e = getenv("VISSAT_FUSE_PAIR"); return !(e && e[0] == '0'); }();
+    if (use_pair) {
+        if (V <= 160) return launch_pair<80>(ctx, views, plane_stride, V, n_cells, out_mean, stream);
+        if (V <= 176) return launch_pair<88>(ctx, views, plane_stride, V, n_cells, out_mean, stream);
+        if (V <= 192) return launch_pair<96>(ctx, views, plane_stride, V, n_cells, out_mean, stream);
+        if (V <= 208) return launch_pair<104>(ctx, views, plane_stride, V, n_cells, out_mean, stream);
+    }
     return launch_large(ctx, views, plane_stride, V, n_cells, out_mean, stream);
 }
 
@@ -939,6 +1125,7 @@ extern "C" int vs_fuse_views_sparse(vs_ctx* ctx, const float* views, int64_t pla
     const int ty_last = (row0 + rows - 1) / VS_TILE_H;
     g.n_units = (ty_last - g.ty_first + 1) * g.tiles_x;
     g.out = out_mean;
+    make_sum_tree(n_views, g);
     // scratch: per-bin counters + per-bin unit lists (grown outside of stream capture: the first call sizes it)
     const size_t need = (size_t)kSparseBins * (1 + (size_t)g.n_units);
     if (ctx->fuse_plan_ints < need) {
@@ -973,8 +1160,8 @@ extern "C" int vs_fuse_views_sparse(vs_ctx* ctx, const float* views, int64_t pla
             case 9: rc = launch_sparse_regs<96>(ctx, g, b, stream); break;
             case 10: rc = launch_sparse_regs<112>(ctx, g, b, stream); break;
             case 11: rc = launch_sparse_regs<128>(ctx, g, b, stream); break;
-            case 12: rc = launch_sparse_large<4, 40>(ctx, g, b, stream); break;
-            case 13: rc = launch_sparse_large<4, 52>(ctx, g, b, stream); break;
+            case 12: rc = launch_sparse_pair<80>(ctx, g, b, stream); break;
+            case 13: rc = launch_sparse_pair<104>(ctx, g, b, stream); break;
             case 14: rc = launch_sparse_large<4, 64>(ctx, g, b, stream); break;
             case 15: rc = launch_sparse_large<8, 52>(ctx, g, b, stream); break;
             case 16: rc = launch_sparse_large<8, 64>(ctx, g, b, stream); break;

@@ -75,6 +75,7 @@ struct vs_ctx {
     size_t scratch_doubles;
     void* d_exact;  // VsExactParams on the device (geo_chain.cuh)
     bool no_tma;    // true unless VISSAT_TMA=1: stage B uses the plain-load kernels (see api.cu)
+    bool k2_legacy; // VISSAT_K2_LEGACY=1 (read at context creation): round-1 float-space stage B instead of finalize_keys.cu
     // vs_views_to_dsm runs odd and even views on two internal streams (stage A of one view overlaps stage B of the
     // previous one: they are bound by different pipes); the odd views scatter into a second, library-owned key grid
     cudaStream_t side_stream[VS_MAX_STREAMS];
