@@ -184,16 +184,29 @@ def test_convert_depth_maps_read_ahead_is_bounded_and_ordered(tmp_path, monkeypa
             live['max'] = max(live['max'], live['loaded'])
         return os.path.basename(path)
 
-    def fake_worker(work_dir, out, item, depth_type, _state=None):
-        if _state['depth_host'] is not None:
-            assert _state['depth_host'] == item           # the prefetched array belongs to this item
-            with lock:
-                live['loaded'] -= 1
-        seen.append(item)
-        return ('dsm', 0, item) if item.endswith('.bin') else None
+    class FakePipeline:
+        """stands in for the GPU side (_ViewPipeline): records the order, releases the prefetched array"""
+
+        def __init__(self, eng, aoi, mats, out, depth_type, n_views, io_pool):
+            assert n_views == 24 and depth_type == 'geometric'   # 23 depth maps + notes.geometric.txt
+            self.views = []
+
+        def submit(self, item, depth_host):
+            if depth_host is not None:
+                assert depth_host == item                 # the prefetched array belongs to this item
+                with lock:
+                    live['loaded'] -= 1
+            seen.append(item)
+            if item.endswith('.bin'):
+                self.views.append((len(self.views), 0, item))
+                return len(self.views) - 1, item
+            return None
+
+        def finish(self):
+            return 'stack', self.views
 
     monkeypatch.setattr(U, 'read_array', fake_read)
-    monkeypatch.setattr(U, 'convert_depth_map_worker', fake_worker)
+    monkeypatch.setattr(U, '_ViewPipeline', FakePipeline)
     monkeypatch.setattr(U, '_make_engine', lambda wd: ('engine', {'aoi': 1}))
     monkeypatch.setattr(U, 'load_inv_proj_mats', lambda d: {})
     U.convert_depth_maps(str(work), str(out_dir), 'geometric', max_processes=3)
@@ -203,6 +216,46 @@ def test_convert_depth_maps_read_ahead_is_bounded_and_ordered(tmp_path, monkeypa
     assert not (out_dir / 'dsm_tif/stale.tif').exists()
     res = U._RESULTS.pop(os.path.abspath(str(out_dir)))
     assert [v[2] for v in res['views']] == [n for n in want if n.endswith('.bin')] and res['world'] == 1
+    assert res['stack'] == 'stack'
+
+
+def test_preview_colour_table_and_psnr(tmp_path):
+    """N3: previews use the reference's colour table with matplotlib's ListedColormap rule (plot_height_map.py:39-57,
+    save_image_only.py:62-101).  The written JPEG is compared (PSNR) with an independent rendering of that rule."""
+    import cv2
+    from vissatsatellitestereo_b200.visualization import plot_height_map as PH
+    from vissatsatellitestereo_b200.visualization._colormap_height import COLORMAP_HEIGHT as LUT
+    assert LUT.shape == (197, 3) and LUT.dtype == np.uint8
+    assert tuple(LUT[0]) == (10, 100, 68) and tuple(LUT[-1]) == (255, 255, 255)        # colormap_height.txt first / last row
+    rng = np.random.default_rng(0)
+    yy, xx = np.mgrid[0:240, 0:320]
+    h = (20 + 15 * np.sin(xx / 40.0) * np.cos(yy / 55.0) + rng.normal(0, 0.2, xx.shape)).astype(np.float32)
+    h[50:80, 100:160] = np.nan
+    out = str(tmp_path / 'p.jpg')
+    PH.plot_height_map(h, out, save_cbar=True)
+    # independent statement of the mapping: percentile range, pins, x = (h - lo) / (hi - lo), index int(x * N) capped
+    lo, hi = np.nanpercentile(h.astype(np.float64), [1, 99])
+    c = np.clip(h.astype(np.float64), lo, hi)
+    c[0, 0], c[0, 1] = lo, hi
+    nan = np.isnan(c)
+    x = (np.where(nan, lo, c) - lo) / (hi - lo)
+    want = np.zeros(h.shape + (3,), dtype=np.uint8)
+    for i in range(h.shape[0]):
+        for j in range(h.shape[1]):
+            want[i, j] = (0, 0, 0) if nan[i, j] else LUT[min(int(x[i, j] * 197), 196)]
+    rgb, mask, rng_used = PH.height_to_rgb(h)
+    assert np.array_equal(rgb, want) and np.array_equal(mask, nan) and rng_used == (lo, hi)
+    assert tuple(rgb[0, 0]) == tuple(LUT[0]) and tuple(rgb[0, 1]) == tuple(LUT[196])
+    got = cv2.imread(out)[:, :, ::-1].astype(np.float64)
+    mse = np.mean((got - want.astype(np.float64)) ** 2)
+    psnr = 10 * np.log10(255.0 ** 2 / mse)
+    assert psnr > 30.0, psnr
+    m = cv2.imread(str(tmp_path / 'p.mask.jpg'), cv2.IMREAD_GRAYSCALE)
+    assert (m[60, 120] < 30) and (m[10, 10] > 225)
+    assert os.path.exists(str(tmp_path / 'p.cbar.jpg'))
+    # force_range and maskout
+    rgb2, mask2, r2 = PH.height_to_rgb(h, force_range=(0.0, 40.0), maskout=(xx < 5))
+    assert r2 == (0.0, 40.0) and mask2[:, :5].all() and (rgb2[:, :5] == 0).all()
 
 
 def _write_tiled_tif(path, a, tile, bo='<', deflate=False):

@@ -19,10 +19,32 @@ from .lib.ply_np_converter import np2ply
 from .produce_dsm import produce_dsm_from_height
 
 
+def _all_ranks_ok(err, device, what):
+    """Under torchrun a rank that raised alone would leave the others inside the next collective: exchange a flag first
+    and fail everywhere."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        if err is not None:
+            raise err
+        return
+    flag = torch.tensor([0 if err is None else 1], dtype=torch.int32, device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+    if err is not None:
+        raise err
+    if int(flag.item()) != 0:
+        raise RuntimeError('{} failed on another rank'.format(what))
+
+
 def run_fuse(work_dir, max_processes=-1):
     # first convert depth maps
     dsm_dir = os.path.join(work_dir, 'colmap/mvs/dsm')
-    convert_depth_maps(work_dir, dsm_dir, depth_type='geometric', max_processes=max_processes)
+    err = None
+    try:
+        convert_depth_maps(work_dir, dsm_dir, depth_type='geometric', max_processes=max_processes)
+    except Exception as e:          # noqa: BLE001 -- re-raised on every rank below
+        err = e
+    dev = torch.device('cuda', torch.cuda.current_device())
+    _all_ranks_ok(err, dev, 'convert_depth_maps')
     res = _util._RESULTS.pop(os.path.abspath(dsm_dir))
     eng, rank, world = res['engine'], res['rank'], res['world']
 
@@ -30,12 +52,11 @@ def run_fuse(work_dir, max_processes=-1):
     if rank == 0:
         os.makedirs(out_dir, exist_ok=True)
 
-    # the per-view DSMs are still on the device, in sorted file order (:59); the reference re-reads the tifs here
-    for dsm, n_nan, stem in res['views']:
-        logging.info('dsm {} empty ratio: {} '.format(stem + '.tif', n_nan / dsm.numel()))
-    views = [v[0] for v in res['views']]
-    local = torch.stack(views) if views else torch.empty((0, eng.n_size, eng.e_size), dtype=torch.float32,
-                                                         device=eng.device)
+    # the per-view DSMs are still on the device, in sorted file order (:59), as planes of ONE stack written by stage B;
+    # the reference re-reads the tifs here
+    local = res['stack']
+    for plane, n_nan, stem in res['views']:
+        logging.info('dsm {} empty ratio: {} '.format(stem + '.tif', n_nan / (eng.n_size * eng.e_size)))
     if world > 1:
         import torch.distributed as dist
         from . import distributed as D
@@ -66,16 +87,14 @@ def run_fuse(work_dir, max_processes=-1):
     xx, yy = np.meshgrid(xx, yy, indexing='ij')
     zz = all_dsm_mean_no_outliers.reshape(-1)
     valid_mask = np.logical_not(np.isnan(zz))
-    color = None
-    try:
-        import cv2
-        bgr = cv2.imread(jpg_to_write) if os.path.exists(jpg_to_write) else None
-        if bgr is not None and bgr.shape[:2] == (n_size, e_size):
-            color = bgr[:, :, ::-1].reshape((-1, 3))
-    except Exception:
-        color = None
-    if color is None:
-        color = np.zeros((zz.size, 3), dtype=np.uint8)
+    # vertex colours: the reference reads its preview jpg back (:100); the same height -> colour mapping (same table, same
+    # alt_min / alt_max clip as produce_dsm_from_height's preview, same [1, 99] percentile range) applied directly, so
+    # the colours neither depend on the previews being written nor carry JPEG noise
+    from .visualization.plot_height_map import height_to_rgb
+    with open(os.path.join(work_dir, 'aoi.json')) as fp:
+        aoi_for_color = json.load(fp)
+    rgb, _, _ = height_to_rgb(np.clip(all_dsm_mean_no_outliers, aoi_for_color['alt_min'], aoi_for_color['alt_max']))
+    color = rgb.reshape((-1, 3))
     utm_points = np.stack((yy.reshape(-1)[valid_mask], xx.reshape(-1)[valid_mask], zz[valid_mask]), axis=1)
     with open(os.path.join(work_dir, 'aoi.json')) as fp:
         aoi_dict = json.load(fp)

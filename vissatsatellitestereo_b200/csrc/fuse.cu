@@ -618,51 +618,143 @@ __device__ __forceinline__ int build_view_list(const uint32_t* __restrict__ occ_
     return s_n;
 }
 
-// numpy's pairwise sum over the ORIGINAL view axis [0, V), one thread per cell, driven by the tile's ascending view list:
-// absent views would add +0, so only the listed ones are visited, each into the accumulator numpy would use
-// (r[(v - leaf offset) % 8] inside the leaf's full blocks of 8, the tail sequentially), leaves folded as the recursion
-// does.  The list is CTA-uniform, so the accumulator switch is a uniform branch.
-__device__ __forceinline__ float sparse_sum_1t(const SparseGeom& g, const int* __restrict__ s_list, int n,
-                                               const float* __restrict__ cellp, float med, float mad) {
-    const KeepFn y{cellp, g.plane_stride, med, mad};
+// numpy's pairwise sum over the ORIGINAL view axis [0, V), driven by the tile's view list.  Absent views would add +0,
+// so only the listed ones are visited.  The list is regrouped once per tile (build_sum_groups, one warp): entries of
+// leaf l that fall into numpy's accumulator r[j] (j = (v - leaf offset) % 8 inside the leaf's full blocks of 8) form
+// group 9 l + j, the leaf's tail elements group 9 l + 8, every group in ascending view order (stable) -- the order
+// numpy adds them in.  The per-cell loop then runs over contiguous ranges with the accumulator in a fixed register.
+constexpr int kMaxGroups = kMaxLeaves * 9;
+
+struct SumGroups {
+    const int* perm;             // shared: plane indices regrouped
+    const unsigned short* gend;  // shared: end offset of every group (cumulative)
+};
+
+// s_perm: >= n ints, s_gend: kMaxGroups ushorts, s_cnt: kMaxGroups ints (scratch).  All threads call it; one warp works.
+__device__ __forceinline__ void build_sum_groups(const SparseGeom& g, const int* __restrict__ s_list, int n, int* s_perm,
+                                                 unsigned short* s_gend, int* s_cnt) {
+    const int tid = threadIdx.x;
+    const int n_groups = g.n_leaves * 9;
+    for (int i = tid; i < n_groups; i += blockDim.x) s_cnt[i] = 0;
+    __syncthreads();
+    if (tid < 32) {
+        const unsigned lt = (1u << tid) - 1u;
+        // pass 1: group sizes
+        for (int i0 = 0; i0 < n; i0 += 32) {
+            const int i = i0 + tid;
+            if (i < n) {
+                const int v = s_list[i];
+                int L = 0;
+                while (L + 1 < g.n_leaves && v >= g.leaf_off[L] + g.leaf_n[L]) ++L;
+                const int pos = v - g.leaf_off[L], nl = g.leaf_n[L];
+                const int j = (nl >= 8 && pos < nl - (nl & 7)) ? (pos & 7) : 8;
+                atomicAdd(&s_cnt[L * 9 + j], 1);
+            }
+        }
+        __syncwarp();
+        // exclusive prefix over the groups -> s_cnt becomes the running write position, s_gend the end offsets
+        int base = 0;
+        for (int q0 = 0; q0 < n_groups; q0 += 32) {
+            const int q = q0 + tid;
+            const int c = q < n_groups ? s_cnt[q] : 0;
+            int incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (tid >= o) incl += t;
+            }
+            if (q < n_groups) {
+                s_cnt[q] = base + incl - c;
+                s_gend[q] = (unsigned short)(base + incl);
+            }
+            base += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        __syncwarp();
+        // pass 2: stable placement, 32 entries at a time (entries of one group keep their ascending order)
+        for (int i0 = 0; i0 < n; i0 += 32) {
+            const int i = i0 + tid;
+            int key = -1 - tid, v = 0;       // inactive lanes: unique keys
+            if (i < n) {
+                v = s_list[i];
+                int L = 0;
+                while (L + 1 < g.n_leaves && v >= g.leaf_off[L] + g.leaf_n[L]) ++L;
+                const int pos = v - g.leaf_off[L], nl = g.leaf_n[L];
+                key = L * 9 + ((nl >= 8 && pos < nl - (nl & 7)) ? (pos & 7) : 8);
+            }
+            const unsigned m = __match_any_sync(0xffffffffu, key);
+            if (i < n) {
+                const int rank = __popc(m & lt);
+                s_perm[s_cnt[key] + rank] = v;
+            }
+            __syncwarp();
+            if (i < n && (m & lt) == 0) s_cnt[key] += __popc(m);      // the group's first lane advances its position
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+}
+
+// One thread sums accumulators [J0, J1) of every leaf (and, if TAIL, adds the tails and folds the leaves); PART = the
+// whole sum when J0 = 0, J1 = 8, TAIL = true.  Returns the partial block sums through r_out when !TAIL.
+__device__ __forceinline__ float kept_value(const float* __restrict__ cellp, int64_t stride, int v, float med, float mad,
+                                            int& cnt) {
+    const float t = __ldg(cellp + (int64_t)v * stride);
+    const bool keep = (t == t) && !(fabsf(__fsub_rn(t, med)) > mad);   // aggregate_2p5d.py:76-77
+    cnt += keep;
+    return keep ? t : 0.0f;
+}
+
+__device__ __forceinline__ float sparse_sum_1t(const SparseGeom& g, const SumGroups& sg, const float* __restrict__ cellp,
+                                               float med, float mad) {
     int e = 0, cnt = 0, sp = 0;
     float st[8];
     for (int L = 0; L < g.n_leaves; ++L) {
-        const int off = g.leaf_off[L], nl = g.leaf_n[L];
-        const int full_end = off + (nl < 8 ? 0 : nl - (nl & 7)), end = off + nl;
-        float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f, r4 = 0.f, r5 = 0.f, r6 = 0.f, r7 = 0.f;
-        while (e < n) {
-            const int v = s_list[e];
-            if (v >= full_end) break;
-            const float t = __ldg(y.p + (int64_t)v * y.stride);
-            const bool keep = (t == t) && !(fabsf(__fsub_rn(t, med)) > mad);
-            const float x = keep ? t : 0.0f;
-            cnt += keep;
-            switch ((v - off) & 7) {      // uniform across the CTA
-                case 0: r0 = __fadd_rn(r0, x); break;
-                case 1: r1 = __fadd_rn(r1, x); break;
-                case 2: r2 = __fadd_rn(r2, x); break;
-                case 3: r3 = __fadd_rn(r3, x); break;
-                case 4: r4 = __fadd_rn(r4, x); break;
-                case 5: r5 = __fadd_rn(r5, x); break;
-                case 6: r6 = __fadd_rn(r6, x); break;
-                default: r7 = __fadd_rn(r7, x); break;
-            }
-            ++e;
+        float r[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            r[j] = 0.0f;
+            const int end = sg.gend[L * 9 + j];
+            for (; e < end; ++e) r[j] = __fadd_rn(r[j], kept_value(cellp, g.plane_stride, sg.perm[e], med, mad, cnt));
         }
-        float res = __fadd_rn(__fadd_rn(__fadd_rn(r0, r1), __fadd_rn(r2, r3)), __fadd_rn(__fadd_rn(r4, r5), __fadd_rn(r6, r7)));
-        while (e < n) {
-            const int v = s_list[e];
-            if (v >= end) break;
-            const float t = __ldg(y.p + (int64_t)v * y.stride);
-            const bool keep = (t == t) && !(fabsf(__fsub_rn(t, med)) > mad);
-            res = __fadd_rn(res, keep ? t : 0.0f);
-            cnt += keep;
-            ++e;
-        }
+        float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                              __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+        const int end = sg.gend[L * 9 + 8];
+        for (; e < end; ++e) res = __fadd_rn(res, kept_value(cellp, g.plane_stride, sg.perm[e], med, mad, cnt));
         for (int q = 0; q < g.leaf_pops[L]; ++q) res = __fadd_rn(st[--sp], res);
         st[sp++] = res;
     }
+    return __fdiv_rn(st[0], (float)cnt);
+}
+
+// The same sum by the two lanes of a pair: lane A owns accumulators 0..3, lane B 4..7 (numpy combines
+// ((r0+r1)+(r2+r3)) + ((r4+r5)+(r6+r7)), so each lane reduces its half and A adds B's); A adds the tails and folds.
+// Returns the mean on lane A.
+__device__ __forceinline__ float sparse_sum_pair(const SparseGeom& g, const SumGroups& sg, const float* __restrict__ cellp,
+                                                 float med, float mad, bool is_b, unsigned pm) {
+    int cnt = 0, sp = 0;
+    float st[8];
+    for (int L = 0; L < g.n_leaves; ++L) {
+        const int j0 = is_b ? 4 : 0;
+        int e = (L * 9 + j0) > 0 ? sg.gend[L * 9 + j0 - 1] : 0;
+        float r[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            r[j] = 0.0f;
+            const int end = sg.gend[L * 9 + j0 + j];
+            for (; e < end; ++e) r[j] = __fadd_rn(r[j], kept_value(cellp, g.plane_stride, sg.perm[e], med, mad, cnt));
+        }
+        const float half = __fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3]));
+        const float other = __shfl_xor_sync(pm, half, 1);
+        float res = __fadd_rn(half, other);              // on A: (A's half) + (B's half), numpy's order
+        if (!is_b) {
+            e = sg.gend[L * 9 + 7];
+            const int end = sg.gend[L * 9 + 8];
+            for (; e < end; ++e) res = __fadd_rn(res, kept_value(cellp, g.plane_stride, sg.perm[e], med, mad, cnt));
+            for (int q = 0; q < g.leaf_pops[L]; ++q) res = __fadd_rn(st[--sp], res);
+            st[sp++] = res;
+        }
+    }
+    cnt += __shfl_xor_sync(pm, cnt, 1);
     return __fdiv_rn(st[0], (float)cnt);
 }
 
@@ -676,14 +768,17 @@ template <int NV>
 __global__ void __launch_bounds__(kBlockSmall, NV <= 32 ? 6 : NV <= 64 ? 5 : NV <= 112 ? 4 : 2)
 k_fuse_sparse_regs(const __grid_constant__ SparseGeom g, int bin) {
     __shared__ uint32_t s_bits[kMaxOccWords];
-    __shared__ int s_list[NV];
+    __shared__ int s_list[NV], s_perm[NV], s_cnt[kMaxGroups];
+    __shared__ unsigned short s_gend[kMaxGroups];
+    const SumGroups sg{s_perm, s_gend};
     const int n_items = g.bin_count[bin] * 4;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int u = g.bin_list[(size_t)bin * g.n_units + (item >> 2)];
         int ty, tx;
         unit_geometry(g, u, ty, tx);
-        __syncthreads();   // the previous item's readers of s_list / s_bits are done
+        __syncthreads();   // the previous item's readers of the shared lists are done
         const int n = build_view_list(g.occ + ((size_t)ty * g.tiles_x + tx) * g.occ_words, g.occ_words, s_bits, s_list, NV);
+        build_sum_groups(g, s_list, n, s_perm, s_gend, s_cnt);
         const int gy0 = max(ty * VS_TILE_H + (item & 3) * 8, g.row0);
         const int gy1 = min(min(ty * VS_TILE_H + (item & 3) * 8 + 8, g.row0 + g.rows), (ty + 1) * VS_TILE_H);
         for (int c = threadIdx.x; c < VS_TILE_W * (gy1 - gy0); c += kBlockSmall) {
@@ -710,7 +805,7 @@ k_fuse_sparse_regs(const __grid_constant__ SparseGeom g, int bin) {
             for (int i = 0; i < NV; ++i) s[i] = fabsf(__fsub_rn(s[i], med));
             bitonic_merge_regs<NV>(s);
             const float mad = middle_of_sorted<NV>(s, k);
-            g.out[cell] = sparse_sum_1t(g, s_list, n, g.views + cell, med, mad);
+            g.out[cell] = sparse_sum_1t(g, sg, g.views + cell, med, mad);
         }
     }
 }
@@ -906,7 +1001,9 @@ template <int NVL>
 __global__ void __launch_bounds__(kPairThreads, 4)
 k_fuse_sparse_pair(const __grid_constant__ SparseGeom g, int bin) {
     __shared__ uint32_t s_bits[kMaxOccWords];
-    __shared__ int s_list[2 * NVL];
+    __shared__ int s_list[2 * NVL], s_perm[2 * NVL], s_cnt[kMaxGroups];
+    __shared__ unsigned short s_gend[kMaxGroups];
+    const SumGroups sg{s_perm, s_gend};
     const int n_items = g.bin_count[bin] * 4;
     const bool is_b = threadIdx.x & 1;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -915,6 +1012,7 @@ k_fuse_sparse_pair(const __grid_constant__ SparseGeom g, int bin) {
         unit_geometry(g, u, ty, tx);
         __syncthreads();
         const int n = build_view_list(g.occ + ((size_t)ty * g.tiles_x + tx) * g.occ_words, g.occ_words, s_bits, s_list, 2 * NVL);
+        build_sum_groups(g, s_list, n, s_perm, s_gend, s_cnt);
         const int gy0 = max(ty * VS_TILE_H + (item & 3) * 8, g.row0);
         const int gy1 = min(min(ty * VS_TILE_H + (item & 3) * 8 + 8, g.row0 + g.rows), (ty + 1) * VS_TILE_H);
         const ListSlot slot{s_list};
@@ -926,8 +1024,12 @@ k_fuse_sparse_pair(const __grid_constant__ SparseGeom g, int bin) {
             float med = 0.f, mad = 0.f;
             int k = 0;
             fuse_cell_pair<NVL>(slot, n, g.views + cell, g.plane_stride, is_b, pm, med, mad, k);
-            if (is_b) continue;
-            g.out[cell] = (k <= 2) ? CUDART_NAN_F : sparse_sum_1t(g, s_list, n, g.views + cell, med, mad);
+            if (k <= 2) {
+                if (!is_b) g.out[cell] = CUDART_NAN_F;
+                continue;
+            }
+            const float mean = sparse_sum_pair(g, sg, g.views + cell, med, mad, is_b, pm);
+            if (!is_b) g.out[cell] = mean;
         }
     }
 }
@@ -936,17 +1038,25 @@ k_fuse_sparse_pair(const __grid_constant__ SparseGeom g, int bin) {
 template <int NVL>
 __global__ void __launch_bounds__(kPairThreads, 4)
 k_fuse_pair(const __grid_constant__ SparseGeom g, int64_t n_cells) {
-    __shared__ int s_list[2 * NVL];
+    __shared__ int s_list[2 * NVL], s_perm[2 * NVL], s_cnt[kMaxGroups];
+    __shared__ unsigned short s_gend[kMaxGroups];
     for (int i = threadIdx.x; i < 2 * NVL; i += kPairThreads) s_list[i] = i;
     __syncthreads();
+    build_sum_groups(g, s_list, g.V, s_perm, s_gend, s_cnt);
+    const SumGroups sg{s_perm, s_gend};
     const bool is_b = threadIdx.x & 1;
     const int64_t cell = blockIdx.x * (int64_t)(kPairThreads / 2) + (threadIdx.x >> 1);
     if (cell >= n_cells) return;
     float med = 0.f, mad = 0.f;
     int k = 0;
-    fuse_cell_pair<NVL>(IdentitySlot(), g.V, g.views + cell, g.plane_stride, is_b, 3u << ((threadIdx.x & 31) & ~1), med, mad, k);
-    if (is_b) return;
-    g.out[cell] = (k <= 2) ? CUDART_NAN_F : sparse_sum_1t(g, s_list, g.V, g.views + cell, med, mad);
+    const unsigned pm = 3u << ((threadIdx.x & 31) & ~1);
+    fuse_cell_pair<NVL>(IdentitySlot(), g.V, g.views + cell, g.plane_stride, is_b, pm, med, mad, k);
+    if (k <= 2) {
+        if (!is_b) g.out[cell] = CUDART_NAN_F;
+        return;
+    }
+    const float mean = sparse_sum_pair(g, sg, g.views + cell, med, mad, is_b, pm);
+    if (!is_b) g.out[cell] = mean;
 }
 
 template <int NVL>
@@ -1159,7 +1269,7 @@ extern "C" int vs_fuse_views_sparse(vs_ctx* ctx, const float* views, int64_t pla
             case 8: rc = launch_sparse_regs<80>(ctx, g, b, stream); break;
             case 9: rc = launch_sparse_regs<96>(ctx, g, b, stream); break;
             case 10: rc = launch_sparse_regs<112>(ctx, g, b, stream); break;
-            case 11: rc = launch_sparse_regs<128>(ctx, g, b, stream); break;
+            case 11: rc = launch_sparse_pair<64>(ctx, g, b, stream); break;     // 113..128: two threads x 64 (255 registers otherwise)
             case 12: rc = launch_sparse_pair<80>(ctx, g, b, stream); break;
             case 13: rc = launch_sparse_pair<104>(ctx, g, b, stream); break;
             case 14: rc = launch_sparse_large<4, 64>(ctx, g, b, stream); break;
