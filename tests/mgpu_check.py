@@ -18,7 +18,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     dist.init_process_group('nccl', device_id=dev)
-    res = mgpu_selfcheck.run(dev, rank, world, log=lambda *a: print(*a, flush=True))
+    res = mgpu_selfcheck.run(dev, rank, world, log=lambda *a: print('[rank {}]'.format(rank), *a, flush=True))
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if res['bit_identical'] else 1)

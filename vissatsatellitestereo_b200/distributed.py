@@ -195,8 +195,10 @@ class PeerExchange:
         my_rows = self.h1 - self.h0
         self.sparse = bool(sparse)
         self.occ_shape = engine.occupancy_shape(self.v_total)                 # full-grid tile indexing on every rank
-        stack_bytes = max(self.v_total * my_rows * self.W * 4, 4)
-        self._occ_offset = (stack_bytes + 255) // 256 * 256                   # bitmap behind the stack, same allocation
+        # the bitmap sits behind the stack in the same allocation, at an offset that is THE SAME ON EVERY RANK (peers
+        # compute each other's bitmap address from it): the largest band stack of any rank, rounded up
+        stack_bytes = max(max(self.v_total * (h1 - h0) * self.W * 4 for (h0, h1) in self.bands_h), 4)
+        self._occ_offset = (stack_bytes + 255) // 256 * 256
         occ_bytes = int(np.prod(self.occ_shape)) * 4
         nbytes = self._occ_offset + occ_bytes
         # Set-up failures must be seen by every rank (a rank that raised alone would leave the others in a collective):

@@ -64,8 +64,11 @@ def check_case(name, grid_w, grid_h, n_views, base, dev, rank, world, log=None):
         px.begin_step()
         eng.views_to_dsm([depth(v) for v in range(a, b)], mats[a:b], px.local)
         band2, (q0, q1) = px.fuse_band()
-        ok_peer &= (q0, q1) == (r0, r1) and _same(px.local, local) and _same(band2, band)
-        ok_peer &= px.check_band_stack(want_stack)
+        checks = {'band_rows': (q0, q1) == (r0, r1), 'local_planes': _same(px.local, local),
+                  'fused_band': _same(band2, band), 'band_stack': px.check_band_stack(want_stack)}
+        if not all(checks.values()) and log:
+            log('MGPU_PEER_DETAIL', name, 'rank', rank, 'step', step, {k: bool(v) for k, v in checks.items()})
+        ok_peer &= all(checks.values())
         torch.cuda.synchronize()
     if px is not None:
         px.close()
