@@ -347,22 +347,61 @@ def measure(cfg, total_views, block, world, rank, dev, steps, warmup, sparse, wa
             dist.barrier()
         torch.cuda.synchronize()
 
-    # One GPU: the whole step (stages A-C) is captured once as a CUDA graph and the timed region replays it
-    # (VISSAT_GRAPH=0: eager launches).  The work is identical; the per-stage breakdown then comes from an eager
-    # instrumented pass right after the timed region.
-    graph, graph_note = None, 'eager launches'
-    if world == 1 and want_graph and os.environ.get('VISSAT_GRAPH', '1') != '0':
-        try:
-            graph = eng.capture_step(depths, mats, stack, fuse=cfg.fuse, occ=occ)
-            graph_note = 'CUDA graph replay ({} kernel launches per step captured once)'.format(graph.launches_per_replay)
-        except Exception as e:
-            graph, graph_note = None, 'eager launches (graph capture failed: {})'.format(str(e)[:120])
-            torch.cuda.synchronize()
-    for _ in range(warmup):
+    # The whole step (stages A-C) is captured once as a CUDA graph and the timed region replays it (VISSAT_GRAPH=0:
+    # eager launches).  The work is identical; the per-stage breakdown then comes from an eager instrumented pass
+    # right after the timed region.  One GPU: one step per graph.  Several GPUs (peer-store exchange): TWO steps per
+    # graph, because the exchange alternates between two band stacks per rank; the stream-ordered barrier between
+    # stage B and the fusion (a 1-element NCCL all-reduce) is captured with the rest.
+    graph, graph_note, steps_per_replay = None, 'eager launches', 1
+    if want_graph and os.environ.get('VISSAT_GRAPH', '1') != '0':
+        if world == 1:
+            try:
+                graph = eng.capture_step(depths, mats, stack, fuse=cfg.fuse, occ=occ)
+                graph_note = 'CUDA graph replay ({} kernel launches per step captured once)'.format(graph.launches_per_replay)
+            except Exception as e:
+                graph, graph_note = None, 'eager launches (graph capture failed: {})'.format(str(e)[:120])
+                torch.cuda.synchronize()
+        elif peer and cfg.fuse:
+            ok = 1
+            try:
+                for _ in range(2):
+                    step(False)                      # lazy allocations (library scratch, NCCL communicator) happen here
+                barrier()
+                n0 = eng.launch_count()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    step(False)
+                    fused_cap = step(False)
+                graph = E.StepGraph(g, fused_cap, eng.launch_count() - n0)
+                steps_per_replay = 2
+            except Exception as e:
+                ok, graph = 0, None
+                graph_note = 'eager launches (graph capture failed: {})'.format(str(e)[:120])
+                torch.cuda.synchronize()
+            t = torch.tensor([ok], dtype=torch.int32, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)              # all ranks replay, or none does
+            if int(t.item()) != 1:
+                graph, steps_per_replay = None, 1
+                if ok:
+                    graph_note = 'eager launches (graph capture failed on another rank)'
+            else:
+                graph_note = 'CUDA graph replay, 2 steps per graph ({} kernel launches + 2 NCCL barriers captured once)'.format(
+                    graph.launches_per_replay)
+
+    def run_steps(k, record):
+        """k steps: graph replays (steps_per_replay each) + eager steps for the remainder"""
+        out = None
+        done = 0
         if graph is not None:
-            graph.replay()
-        else:
-            step(False)
+            while done + steps_per_replay <= k:
+                out = graph.replay()
+                done += steps_per_replay
+        while done < k:
+            out = step(record and graph is None)
+            done += 1
+        return out
+
+    run_steps(warmup, False)
     barrier()
     launches0 = eng.launch_count()
     if graph is None:
@@ -370,11 +409,14 @@ def measure(cfg, total_views, block, world, rank, dev, steps, warmup, sparse, wa
     t0, t1 = ev(), ev()
     barrier()
     t0.record()
-    for _ in range(steps):
-        fused = graph.replay() if graph is not None else step(True)
+    fused = run_steps(steps, True)
     t1.record()
     barrier()
-    launches = graph.launches_per_replay * steps if graph is not None else eng.launch_count() - launches0
+    if graph is not None:
+        n_rep = steps // steps_per_replay
+        launches = graph.launches_per_replay * n_rep + (eng.launch_count() - launches0)
+    else:
+        launches = eng.launch_count() - launches0
     ms_total = t0.elapsed_time(t1)
     if world > 1:
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
