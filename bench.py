@@ -352,7 +352,7 @@ def measure(cfg, total_views, block, world, rank, dev, steps, warmup, sparse, wa
     # right after the timed region.  One GPU: one step per graph.  Several GPUs (peer-store exchange): TWO steps per
     # graph, because the exchange alternates between two band stacks per rank; the stream-ordered barrier between
     # stage B and the fusion (a 1-element NCCL all-reduce) is captured with the rest.
-    graph, graph_note, steps_per_replay = None, 'eager launches', 1
+    graph, graph_note, steps_per_replay, graph_parity = None, 'eager launches', 1, 0
     if want_graph and os.environ.get('VISSAT_GRAPH', '1') != '0':
         if world == 1:
             try:
@@ -368,6 +368,7 @@ def measure(cfg, total_views, block, world, rank, dev, steps, warmup, sparse, wa
                     step(False)                      # lazy allocations (library scratch, NCCL communicator) happen here
                 barrier()
                 n0 = eng.launch_count()
+                graph_parity = xch._cur % 2          # the captured pair starts with the OTHER band stack
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     step(False)
@@ -392,6 +393,11 @@ def measure(cfg, total_views, block, world, rank, dev, steps, warmup, sparse, wa
         """k steps: graph replays (steps_per_replay each) + eager steps for the remainder"""
         out = None
         done = 0
+        if graph is not None and steps_per_replay == 2 and k > 0 and xch._cur % 2 != graph_parity:
+            # an odd number of eager steps since the capture: the graph's first step would reuse the band stack the last
+            # eager step wrote (its owner may still be fusing it).  One eager step restores the alternation.
+            out = step(False)
+            done = 1
         if graph is not None:
             while done + steps_per_replay <= k:
                 out = graph.replay()
