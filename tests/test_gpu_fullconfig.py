@@ -81,6 +81,11 @@ def _oracle_bands(depths, mats, aoi, cfg, bands, skip_far_views=False):
     return [r[0] for r in res], [r[1] for r in res]
 
 
+def _occupancy_fraction(occ, V):
+    g = torch.arange(V, device=occ.device)
+    return (((occ[:, :, g // 32] >> (g % 32).to(torch.int32)) & 1).float().mean()).item()
+
+
 def _allow_mask(cells, rb, re, e_size, radius=3):
     """Cells within `radius` of a cell an ambiguous point may enter or leave (band-local coordinates)."""
     m = np.zeros((re - rb, e_size), dtype=np.uint8)
@@ -118,7 +123,8 @@ def _compare_fused(tag, got, want, oracle_views_h, allow, report, top=0):
         tag, int(unexplained.sum()), HEIGHT_TOL, np.argwhere(unexplained)[:5])
 
 
-def _run_config(name, bands, lanes, views=None, per_view_only=False, check_views=None, skip_far_views=False):
+def _run_config(name, bands, lanes, views=None, per_view_only=False, check_views=None, skip_far_views=False,
+                also_sparse=False):
     from vissatsatellitestereo_b200 import engine as E
     from vissatsatellitestereo_b200 import synthetic as S
     V_all = S.CONFIGS[name].n_views
@@ -134,6 +140,23 @@ def _run_config(name, bands, lanes, views=None, per_view_only=False, check_views
     st = stats.cpu().numpy()
     fused = None if per_view_only else eng.fuse_and_blur(stack)
     torch.cuda.synchronize()
+    if also_sparse:
+        # the sparse path (stage A marks touched tiles, stage B / the key-grid clear / the fusion visit only those) must
+        # give the same per-view planes and the same fused DSM, bit for bit, at the config's full size
+        occ = eng.alloc_occupancy(V)
+        eng.set_occupancy(occ, stack, 0)
+        keep = fused.clone()
+        stack.fill_(-7.0)
+        for rep in range(2):                       # twice: the tile-wise key-grid clear must leave the grids empty
+            occ.zero_()
+            eng.views_to_dsm(depths, mats, stack)
+        eng.set_occupancy(None)
+        fused_sparse = eng.median3x3(eng.fuse(stack, occ=occ), count_nan=True)
+        assert torch.equal(torch.nan_to_num(fused_sparse, nan=-1e9), torch.nan_to_num(keep, nan=-1e9)), \
+            '{}: sparse path differs from the dense path'.format(name)
+        print('[{}] sparse path: bit-identical to the dense path; tile occupancy {:.3f}'.format(
+            name, float(_occupancy_fraction(occ, V))))
+        del occ, keep, fused_sparse
 
     bands_h = [(max(rb - 1, 0), min(re + 1, n)) for rb, re in bands]          # + blur halo for the fused rows
     want_views, infos = _oracle_bands(depths, mats, aoi, cfg, bands_h, skip_far_views=skip_far_views)
@@ -222,4 +245,4 @@ def test_c4_four_views_per_view_only(lanes):
 def test_c3_all_200_views_fused_bands(lanes):
     """C3 (200 x 4096^2 -> 8192^2 @ 0.3 m): every view covers ~1/3 of the rows; fused rows with V = 200, and the
     per-view rows of the first 3 views that reach each band plus 3 fixed ones."""
-    _run_config('C3', [(0, 12), (4090, 4102), (8180, 8192)], lanes, skip_far_views=True)
+    _run_config('C3', [(0, 12), (4090, 4102), (8180, 8192)], lanes, skip_far_views=True, also_sparse=True)

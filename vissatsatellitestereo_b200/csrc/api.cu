@@ -144,6 +144,9 @@ int vs_ctx_create(int device, vs_ctx** out) {
     ctx->occ_view0 = 0;
     ctx->d_fuse_plan = nullptr;
     ctx->fuse_plan_ints = 0;
+    for (int i = 0; i < VS_MAX_STREAMS; ++i) ctx->d_touched[i] = nullptr;
+    ctx->touched_tiles = 0;
+    ctx->cur_touched = nullptr;
     for (int i = 0; i < VS_MAX_STREAMS; ++i) {
         ctx->side_stream[i] = nullptr;
         ctx->join_event[i] = nullptr;
@@ -162,6 +165,8 @@ int vs_ctx_create(int device, vs_ctx** out) {
         // shared-memory pass and the kernel is ALU-bound, not load-latency-bound), so it is opt-in.
         const char* e = getenv("VISSAT_TMA");
         ctx->no_tma = !(e != nullptr && e[0] == '1');
+        const char* wa = getenv("VISSAT_K1_WARPAGG");
+        ctx->k1_warp_agg = wa != nullptr && wa[0] == '1';
         const char* l = getenv("VISSAT_K2_LEGACY");
         ctx->k2_legacy = l != nullptr && l[0] == '1';
     }
@@ -176,6 +181,8 @@ int vs_ctx_destroy(vs_ctx* ctx) {
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     if (ctx->d_exact) cudaFree(ctx->d_exact);
     if (ctx->d_fuse_plan) cudaFree(ctx->d_fuse_plan);
+    for (int i = 0; i < VS_MAX_STREAMS; ++i)
+        if (ctx->d_touched[i]) cudaFree(ctx->d_touched[i]);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     for (int i = 0; i < VS_MAX_STREAMS; ++i) {
         if (ctx->side_stream[i]) cudaStreamDestroy(ctx->side_stream[i]);

@@ -321,9 +321,11 @@ k_median3x3(const float* __restrict__ in, int in_row0, int H, int W, int row_beg
 int vs_launch_finalize_keys(vs_ctx* ctx, const uint32_t* keygrid, int xsize, int ysize, float* dsm_out, int simd_cols,
                             unsigned long long* nan_count, cudaStream_t stream);
 int vs_launch_finalize_keys_occ(vs_ctx* ctx, const uint32_t* keygrid, int xsize, int ysize, float* dsm_out, int simd_cols,
-                                unsigned long long* nan_count, const VsOccPlan& plan, cudaStream_t stream);
+                                unsigned long long* nan_count, const VsOccPlan& plan, const unsigned char* touched,
+                                cudaStream_t stream);
 int vs_launch_finalize_keys_peer(vs_ctx* ctx, const uint32_t* keygrid, int xsize, int ysize, float* dsm_out, int simd_cols,
-                                 unsigned long long* nan_count, const VsPeerPlan& plan, cudaStream_t stream);
+                                 unsigned long long* nan_count, const VsPeerPlan& plan, const unsigned char* touched,
+                                 cudaStream_t stream);
 
 // Stage B of one view with the peer stores of the multi-GPU exchange (called by vs_views_to_dsm, pipeline.cu).
 int vs_grid_finalize_peer(vs_ctx* ctx, const uint32_t* keygrid, int xsize, int ysize, float* dsm_out, int simd_lanes,
@@ -331,7 +333,7 @@ int vs_grid_finalize_peer(vs_ctx* ctx, const uint32_t* keygrid, int xsize, int y
     if (nan_count) VS_CUDA(cudaMemsetAsync(nan_count, 0, sizeof(uint64_t), stream));
     if (!ctx->k2_legacy)
         return vs_launch_finalize_keys_peer(ctx, keygrid, xsize, ysize, dsm_out, simd_cols_for(xsize, simd_lanes),
-                                            reinterpret_cast<unsigned long long*>(nan_count), plan, stream);
+                                            reinterpret_cast<unsigned long long*>(nan_count), plan, ctx->cur_touched, stream);
     PeerSink sink;
     sink.p = plan;
     dim3 grid((xsize + TW - 1) / TW, (ysize + TH - 1) / TH);
@@ -349,7 +351,7 @@ int vs_grid_finalize_occ(vs_ctx* ctx, const uint32_t* keygrid, int xsize, int ys
     if (nan_count) VS_CUDA(cudaMemsetAsync(nan_count, 0, sizeof(uint64_t), stream));
     if (!ctx->k2_legacy)
         return vs_launch_finalize_keys_occ(ctx, keygrid, xsize, ysize, dsm_out, simd_cols_for(xsize, simd_lanes),
-                                           reinterpret_cast<unsigned long long*>(nan_count), plan, stream);
+                                           reinterpret_cast<unsigned long long*>(nan_count), plan, ctx->cur_touched, stream);
     OccSink sink;
     sink.o = plan;
     dim3 grid((xsize + TW - 1) / TW, (ysize + TH - 1) / TH);

@@ -81,6 +81,7 @@ struct NoSink {
     __device__ __forceinline__ void store1(int, int, int, float) const {}
     __device__ __forceinline__ void mark_tile(int, int, int) const {}       // one thread per CTA calls it
     __device__ __forceinline__ bool skips_empty_tiles() const { return false; }
+    __device__ __forceinline__ bool skips_empty_tiles_or_none() const { return true; }   // nothing goes to peers
 };
 // Records which (tile, view) pairs hold data (vs_set_occupancy); no peer stores.
 struct OccSink {
@@ -91,12 +92,14 @@ struct OccSink {
         atomicOr(o.occ + ((size_t)ty * o.tiles_x + tx) * o.occ_words + (o.view >> 5), 1u << (o.view & 31));
     }
     __device__ __forceinline__ bool skips_empty_tiles() const { return false; }
+    __device__ __forceinline__ bool skips_empty_tiles_or_none() const { return true; }
 };
 struct PeerSink {
     VsPeerPlan p;
     // sparse exchange: an all-empty tile is not stored into the band stacks; a tile with data sets its (tile, view)
     // bit in the bitmap of every rank whose band (+ halo) it touches (system-scope atomics over NVLink)
     __device__ __forceinline__ bool skips_empty_tiles() const { return p.occ_words > 0; }
+    __device__ __forceinline__ bool skips_empty_tiles_or_none() const { return p.occ_words > 0; }
     __device__ __forceinline__ void mark_tile(int tx, int ty, int H) const {
         if (p.occ_words <= 0) return;
         const int y0 = ty * TH, y1 = min(y0 + TH, H) - 1;

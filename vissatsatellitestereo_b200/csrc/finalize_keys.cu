@@ -178,6 +178,17 @@ template <typename Sink>
 __device__ __forceinline__ void write_nan_tile_keys(float* __restrict__ blur_out, int ty0, int tx0, int H, int W,
                                                     unsigned long long* __restrict__ nan_count, const Sink& sink) {
     unsigned n = 0;
+    // full tile of a 16-byte-pitch grid with nothing to forward to peers: 2 float4 stores per thread
+    if (sink.skips_empty_tiles_or_none() && (W & 3) == 0 && ((reinterpret_cast<uintptr_t>(blur_out) & 15) == 0) &&
+        tx0 + TW <= W && ty0 + TH <= H) {
+        const float4 nan4 = make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F);
+        for (int i = threadIdx.x; i < TW * TH / 4; i += kThreads) {
+            const int r = i / (TW / 4), c4 = i - r * (TW / 4);
+            *reinterpret_cast<float4*>(blur_out + (size_t)(ty0 + r) * W + tx0 + 4 * c4) = nan4;
+        }
+        if (nan_count != nullptr && threadIdx.x == 0) atomicAdd(nan_count, (unsigned long long)(TW * TH));
+        return;
+    }
     for (int i = threadIdx.x; i < TW * TH; i += kThreads) {
         const int r = i / TW, c = i - r * TW;
         const int gy = ty0 + r, gx = tx0 + c;
@@ -190,10 +201,35 @@ __device__ __forceinline__ void write_nan_tile_keys(float* __restrict__ blur_out
     block_count_flush(n, nan_count);
 }
 
+// Sparse mode: zero the keys of the tiles stage A touched and reset their marks -- replaces the whole-grid memset
+// between views (on a large AOI a view touches about a third of the tiles).
+__global__ void __launch_bounds__(kThreads)
+k_clear_touched(uint32_t* __restrict__ keygrid, unsigned char* __restrict__ touched, int W, int H, int tiles_x, int n_tiles) {
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const bool on = touched[t] != 0;
+        __syncthreads();                     // everybody has read the mark before thread 0 resets it
+        if (!on) continue;                   // block-uniform
+        const int ty0 = (t / tiles_x) * TH, tx0 = (t - (t / tiles_x) * tiles_x) * TW;
+        if ((W & 3) == 0 && ((reinterpret_cast<uintptr_t>(keygrid) & 15) == 0) && tx0 + TW <= W && ty0 + TH <= H) {
+            for (int i = threadIdx.x; i < TW * TH / 4; i += kThreads) {
+                const int r = i / (TW / 4), c4 = i - r * (TW / 4);
+                *reinterpret_cast<uint4*>(keygrid + (size_t)(ty0 + r) * W + tx0 + 4 * c4) = make_uint4(0u, 0u, 0u, 0u);
+            }
+        } else {
+            for (int i = threadIdx.x; i < TW * TH; i += kThreads) {
+                const int r = i / TW, c = i - r * TW;
+                if (ty0 + r < H && tx0 + c < W) keygrid[(size_t)(ty0 + r) * W + tx0 + c] = 0u;
+            }
+        }
+        if (threadIdx.x == 0) touched[t] = 0;
+    }
+}
+
 template <typename Sink>
 __global__ void __launch_bounds__(kThreads, 5)
 k_grid_finalize_keys(const uint32_t* __restrict__ keygrid, int W, int H, float* __restrict__ blur_out, int simd_cols,
-                     unsigned long long* __restrict__ nan_count, const __grid_constant__ Sink sink) {
+                     unsigned long long* __restrict__ nan_count, const unsigned char* __restrict__ touched,
+                     const __grid_constant__ Sink sink) {
     __shared__ __align__(16) uint32_t s_key[TR * TS];   // keys of the tile + 2-cell halo; holes are patched in place
     __shared__ unsigned short s_hole_pos[MAX_HOLES];
     __shared__ uint32_t s_hole_val[MAX_HOLES];
@@ -202,6 +238,17 @@ k_grid_finalize_keys(const uint32_t* __restrict__ keygrid, int W, int H, float* 
     const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH;
     if (tid == 0) s_has_nan = 0;
     __syncthreads();
+    if (touched != nullptr) {   // sparse mode: a tile whose 3x3 tile neighbourhood got no key is empty without looking
+        int any = 0;
+        if (tid < 9) {
+            const int ty = (int)blockIdx.y + tid / 3 - 1, tx = (int)blockIdx.x + tid % 3 - 1;
+            if (ty >= 0 && ty < (int)gridDim.y && tx >= 0 && tx < (int)gridDim.x) any = touched[ty * gridDim.x + tx];
+        }
+        if (!__syncthreads_or(any)) {
+            write_nan_tile_keys(blur_out, ty0, tx0, H, W, nan_count, sink);
+            return;
+        }
+    }
 
     // 1. load the keys (+2 halo; key 0 = empty, also used outside the grid) and list the holes = empty cells inside
     //    the grid within the 1-cell halo of the tile.  Every warp keeps its own list (count in a register).
@@ -350,28 +397,37 @@ k_grid_finalize_keys(const uint32_t* __restrict__ keygrid, int W, int H, float* 
 }  // namespace
 
 // Launchers used by finalize.cu's entry points (one per sink).
+int vs_launch_clear_touched(vs_ctx* ctx, uint32_t* keygrid, unsigned char* touched, int xsize, int ysize, cudaStream_t stream) {
+    const int tiles_x = (xsize + TW - 1) / TW, n_tiles = tiles_x * ((ysize + TH - 1) / TH);
+    const int blocks = n_tiles < ctx->sm_count * 8 ? n_tiles : ctx->sm_count * 8;
+    k_clear_touched<<<blocks, kThreads, 0, stream>>>(keygrid, touched, xsize, ysize, tiles_x, n_tiles);
+    VS_CHECK_LAUNCH(ctx, "k_clear_touched");
+    return VS_OK;
+}
 int vs_launch_finalize_keys(vs_ctx* ctx, const uint32_t* keygrid, int xsize, int ysize, float* dsm_out, int simd_cols,
                             unsigned long long* nan_count, cudaStream_t stream) {
     dim3 grid((xsize + TW - 1) / TW, (ysize + TH - 1) / TH);
-    k_grid_finalize_keys<NoSink><<<grid, kThreads, 0, stream>>>(keygrid, xsize, ysize, dsm_out, simd_cols, nan_count, NoSink());
+    k_grid_finalize_keys<NoSink><<<grid, kThreads, 0, stream>>>(keygrid, xsize, ysize, dsm_out, simd_cols, nan_count, nullptr, NoSink());
     VS_CHECK_LAUNCH(ctx, "k_grid_finalize_keys");
     return VS_OK;
 }
 int vs_launch_finalize_keys_occ(vs_ctx* ctx, const uint32_t* keygrid, int xsize, int ysize, float* dsm_out, int simd_cols,
-                                unsigned long long* nan_count, const VsOccPlan& plan, cudaStream_t stream) {
+                                unsigned long long* nan_count, const VsOccPlan& plan, const unsigned char* touched,
+                                cudaStream_t stream) {
     OccSink sink;
     sink.o = plan;
     dim3 grid((xsize + TW - 1) / TW, (ysize + TH - 1) / TH);
-    k_grid_finalize_keys<OccSink><<<grid, kThreads, 0, stream>>>(keygrid, xsize, ysize, dsm_out, simd_cols, nan_count, sink);
+    k_grid_finalize_keys<OccSink><<<grid, kThreads, 0, stream>>>(keygrid, xsize, ysize, dsm_out, simd_cols, nan_count, touched, sink);
     VS_CHECK_LAUNCH(ctx, "k_grid_finalize_keys<occ>");
     return VS_OK;
 }
 int vs_launch_finalize_keys_peer(vs_ctx* ctx, const uint32_t* keygrid, int xsize, int ysize, float* dsm_out, int simd_cols,
-                                 unsigned long long* nan_count, const VsPeerPlan& plan, cudaStream_t stream) {
+                                 unsigned long long* nan_count, const VsPeerPlan& plan, const unsigned char* touched,
+                                 cudaStream_t stream) {
     PeerSink sink;
     sink.p = plan;
     dim3 grid((xsize + TW - 1) / TW, (ysize + TH - 1) / TH);
-    k_grid_finalize_keys<PeerSink><<<grid, kThreads, 0, stream>>>(keygrid, xsize, ysize, dsm_out, simd_cols, nan_count, sink);
+    k_grid_finalize_keys<PeerSink><<<grid, kThreads, 0, stream>>>(keygrid, xsize, ysize, dsm_out, simd_cols, nan_count, touched, sink);
     VS_CHECK_LAUNCH(ctx, "k_grid_finalize_keys<peer>");
     return VS_OK;
 }

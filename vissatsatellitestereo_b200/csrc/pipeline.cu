@@ -6,6 +6,7 @@ int vs_grid_finalize_peer(vs_ctx* ctx, const uint32_t* keygrid, int xsize, int y
                           uint64_t* nan_count, const VsPeerPlan& plan, cudaStream_t stream);
 int vs_grid_finalize_occ(vs_ctx* ctx, const uint32_t* keygrid, int xsize, int ysize, float* dsm_out, int simd_lanes,
                          uint64_t* nan_count, const VsOccPlan& plan, cudaStream_t stream);
+int vs_launch_clear_touched(vs_ctx* ctx, uint32_t* keygrid, unsigned char* touched, int xsize, int ysize, cudaStream_t stream);
 
 extern "C" {
 
@@ -58,6 +59,30 @@ int vs_views_to_dsm(vs_ctx* ctx, int32_t n_views, const float* const* depth, con
         VS_CUDA(cudaEventRecord(ctx->fork_event, stream));
         for (int i = 0; i < NS; ++i) VS_CUDA(cudaStreamWaitEvent(ctx->side_stream[i], ctx->fork_event, 0));
     }
+    // Sparse mode (an occupancy bitmap is being written: large AOIs where a view covers part of the grid): stage A marks
+    // the tiles it puts keys into, stage B looks only at tiles with a marked neighbour, and the key grid is cleared
+    // tile by tile after stage B instead of by a whole-grid memset per view.  The key grids are zeroed once per call.
+    const bool sparse = !ctx->k2_legacy && ctx->poly.degree > 0 &&
+                        (ctx->xch_on ? ctx->xch.occ_words > 0 : ctx->occ != nullptr);
+    const size_t n_tiles = (size_t)((xs + VS_TILE_W - 1) / VS_TILE_W) * ((ys + VS_TILE_H - 1) / VS_TILE_H);
+    if (sparse) {
+        if (ctx->touched_tiles < n_tiles) {
+            for (int i = 0; i < VS_MAX_STREAMS; ++i) {
+                if (ctx->d_touched[i]) cudaFree(ctx->d_touched[i]);
+                ctx->d_touched[i] = nullptr;
+            }
+            ctx->touched_tiles = 0;
+        }
+        const int n_used = dual ? NS : 1;
+        for (int i = 0; i < n_used; ++i)
+            if (!ctx->d_touched[i]) VS_CUDA(cudaMalloc(&ctx->d_touched[i], n_tiles));
+        ctx->touched_tiles = n_tiles;
+        for (int i = 0; i < n_used; ++i) {
+            cudaStream_t st = dual ? ctx->side_stream[i] : stream;
+            VS_CUDA(cudaMemsetAsync(i ? ctx->d_keygrid_extra[i] : keygrid, 0, (size_t)xs * ys * sizeof(uint32_t), st));
+            VS_CUDA(cudaMemsetAsync(ctx->d_touched[i], 0, n_tiles, st));
+        }
+    }
     // On a per-view error the loop stops, but the side streams are still joined into the caller's stream below: the
     // work already enqueued stays ordered before whatever the caller enqueues next (and a stream capture in progress
     // stays joinable).  Planes [0, v) of dsm_stack are then complete, plane v onwards is undefined.
@@ -66,8 +91,11 @@ int vs_views_to_dsm(vs_ctx* ctx, int32_t n_views, const float* const* depth, con
         const int si = dual ? v % NS : 0;
         cudaStream_t st = dual ? ctx->side_stream[si] : stream;
         uint32_t* kg = si ? ctx->d_keygrid_extra[si] : keygrid;
-        rc = vs_keygrid_clear(ctx, kg, (int64_t)xs * ys, 4, st);
-        if (rc) break;
+        ctx->cur_touched = sparse ? ctx->d_touched[si] : nullptr;
+        if (!sparse) {
+            rc = vs_keygrid_clear(ctx, kg, (int64_t)xs * ys, 4, st);
+            if (rc) break;
+        }
         if (ctx->timing && cudaEventRecord(ctx->ev_pool[ctx->ev_used + 0], st) != cudaSuccess) { rc = vs_cuda_fail(cudaGetLastError(), "cudaEventRecord"); break; }
         rc = vs_unproject_rasterize(ctx, depth[v], H[v], W[v], inv_proj_mats + 16 * (size_t)v, kg, 0, nullptr,
                                     stats ? stats + (size_t)v * VS_NUM_STATS : nullptr, st);
@@ -100,11 +128,16 @@ int vs_views_to_dsm(vs_ctx* ctx, int32_t n_views, const float* const* depth, con
             rc = vs_grid_finalize(ctx, kg, xs, ys, plane, simd_lanes, nan_counts ? nan_counts + v : nullptr, st);
         }
         if (rc) break;
+        if (sparse) {   // leave the key grid of this stream empty again: clear the touched tiles, reset their marks
+            rc = vs_launch_clear_touched(ctx, kg, ctx->d_touched[si], xs, ys, st);
+            if (rc) break;
+        }
         if (ctx->timing) {
             if (cudaEventRecord(ctx->ev_pool[ctx->ev_used + 2], st) != cudaSuccess) { rc = vs_cuda_fail(cudaGetLastError(), "cudaEventRecord"); break; }
             ctx->ev_used += 3;
         }
     }
+    ctx->cur_touched = nullptr;
     if (dual) {
         const std::string first_error = rc ? std::string(vs_last_error()) : std::string();
         for (int i = 0; i < NS; ++i) {

@@ -29,6 +29,10 @@ struct RasterParams {
     int H, W;
     int xsize, ysize;
     int degree;
+    int warp_agg;                // VISSAT_K1_WARPAGG=1: warp-aggregated scatter (A/B variant, see the scatter below)
+    int tiles_x;                 // sparse mode: tile columns of the touched map
+    unsigned char* touched;      // sparse mode (large AOIs): one byte per 64x32 tile, set when a key lands in the tile, so
+                                 // that stage B and the key-grid clear visit only those tiles (nullptr: off)
     unsigned long long w_magic;  // ceil(2^48 / W)
 };
 
@@ -70,12 +74,20 @@ __device__ __forceinline__ void flush_stats(unsigned long long* stats, unsigned 
     if (threadIdx.x < 4 && s_acc[threadIdx.x]) atomicAdd(&stats[threadIdx.x], (unsigned long long)s_acc[threadIdx.x]);
 }
 
+// Sparse mode: remember that a key landed in this tile.  Plain cached load + conditional store of a constant: a stale
+// 0 only costs a redundant store, and a byte never goes back to 0 while a stage-A kernel runs.
+__device__ __forceinline__ void mark_touched(unsigned char* __restrict__ touched, int tiles_x, int ri, int ci) {
+    unsigned char* t = touched + (ri >> 5) * tiles_x + (ci >> 6);
+    if (*t == 0) *t = 1;
+}
+
 // Rare per-point slow path of K1 (point outside the fitted altitude range): exact chain, kept out of line and
 // fed from one device-memory parameter block so that it costs the streaming path neither registers nor a
 // stack copy of the kernel parameters.  Returns 1 if the point landed in the grid, 2 if it is also within
 // eps of a cell edge.
 __device__ __noinline__ int scatter_exact_point(const VsExactParams* __restrict__ ex, double u, double v, double w,
-                                                uint32_t* __restrict__ keygrid) {
+                                                uint32_t* __restrict__ keygrid, unsigned char* __restrict__ touched,
+                                                int tiles_x) {
     double E, N, A;
     const VsGeoParams& g = ex->g;
     vs_enu_to_utm_exact(ex->c, g, fma(u, ex->half[0], ex->center[0]), fma(v, ex->half[1], ex->center[1]),
@@ -84,6 +96,7 @@ __device__ __noinline__ int scatter_exact_point(const VsExactParams* __restrict_
     const double cfl = floor(colf), rfl = floor(rowf);
     if (cfl >= 0.0 && rfl >= 0.0 && cfl < (double)g.xsize && rfl < (double)g.ysize && A == A) {
         atomicMax(keygrid + ((int)rfl * g.xsize + (int)cfl), vs_key32((float)A));
+        if (touched != nullptr) mark_touched(touched, tiles_x, (int)rfl, (int)cfl);
         const double fcx = colf - cfl, frx = rowf - rfl;
         const double eps = ex->eps;
         return (fcx < eps || fcx > 1.0 - eps || frx < eps || frx > 1.0 - eps) ? 2 : 1;
@@ -156,10 +169,11 @@ __device__ __forceinline__ void scatter_chunk_generic(const RasterParams& p, con
                             if (audit && (fabs(val[0][0] - rint(val[0][0])) < p.eps || fabs(val[1][0] - rint(val[1][0])) < p.eps))
                                 ++cnt[VS_STAT_AMBIGUOUS];
                             atomicMax(keygrid + (ri * p.xsize + ci), vs_key32((float)val[2][0]));
+                            if (p.touched != nullptr) mark_touched(p.touched, p.tiles_x, ri, ci);
                         }
                     } else {
                         ++cnt[VS_STAT_EXACT];
-                        const int r = scatter_exact_point(ex, u[0], v[0], w[0], keygrid);
+                        const int r = scatter_exact_point(ex, u[0], v[0], w[0], keygrid, p.touched, p.tiles_x);
                         cnt[VS_STAT_INGRID] += (r != 0);
                         cnt[VS_STAT_AMBIGUOUS] += (r == 2);
                     }
@@ -314,15 +328,44 @@ k_unproject_scatter(RasterParams p, PolyCoefs pc, const VsExactParams* __restric
                 cnt[VS_STAT_AMBIGUOUS] += fast[i] && amb[i];
             }
         }
+        if (p.touched != nullptr) {   // block-uniform: sparse mode
+            int prev = -1;
+#pragma unroll
+            for (int i = 0; i < PX; ++i) {
+                const int t = (ri[i] >> 5) * p.tiles_x + (ci[i] >> 6);
+                if (fast[i] && t != prev) {
+                    unsigned char* q = p.touched + t;
+                    if (*q == 0) *q = 1;
+                    prev = t;
+                }
+            }
+        }
 #pragma unroll
         for (int i = 0; i + 1 < PX; ++i) {
             const bool same = fast[i] && fast[i + 1] && cell[i] == cell[i + 1];
             key[i + 1] = same ? max(key[i + 1], key[i]) : key[i + 1];
             fast[i] = fast[i] && !same;
         }
+        if (p.warp_agg) {
+            // A/B variant (north_star item 3, "warp-aggregated atomics"): lanes of the warp that hit the same cell are
+            // found with match.any, their keys reduced with redux.max, and one lane issues the atomic.  Measured on
+            // C4 (4 pixels per cell) and C2: see profiles/README.md -- a warp covers 128 consecutive pixels of ONE
+            // image row, so only neighbouring lanes ever share a cell; the in-thread merge above already removes most
+            // duplicates and the match costs more than the atomics it saves.  Kept switchable, off by default.
+            const unsigned lane = threadIdx.x & 31;
 #pragma unroll
-        for (int i = 0; i < PX; ++i)
-            if (fast[i]) atomicMax(keygrid + cell[i], key[i]);
+            for (int i = 0; i < PX; ++i) {
+                const unsigned act = __activemask();
+                const int tag = fast[i] ? cell[i] : -1 - (int)lane;
+                const unsigned grp = __match_any_sync(act, tag);
+                const uint32_t best = __reduce_max_sync(grp, key[i]);
+                if (fast[i] && lane == (unsigned)(__ffs(grp) - 1)) atomicMax(keygrid + cell[i], best);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < PX; ++i)
+                if (fast[i]) atomicMax(keygrid + cell[i], key[i]);
+        }
 
         if (any_slow) {  // points outside the fitted altitude range: exact chain, out of line (rare)
 #pragma unroll
@@ -330,7 +373,7 @@ k_unproject_scatter(RasterParams p, PolyCoefs pc, const VsExactParams* __restric
                 if (d4[i] > 0.0f && fabsf(uf[i]) <= 1.0f && fabsf(vf[i]) <= 1.0f && !(fabsf(wf[i]) <= 1.0f) &&
                     fabsf(wf[i]) < CUDART_INF_F) {
                     ++cnt[VS_STAT_EXACT];
-                    const int r = scatter_exact_point(ex, u[i], v[i], w[i], keygrid);
+                    const int r = scatter_exact_point(ex, u[i], v[i], w[i], keygrid, p.touched, p.tiles_x);
                     cnt[VS_STAT_INGRID] += (r != 0);
                     cnt[VS_STAT_AMBIGUOUS] += (r == 2);
                 }
@@ -451,6 +494,9 @@ int vs_unproject_rasterize(vs_ctx* ctx, const float* depth, int32_t H, int32_t W
     p.xsize = ctx->aoi.xsize;
     p.ysize = ctx->aoi.ysize;
     p.degree = P.degree;
+    p.warp_agg = ctx->k1_warp_agg ? 1 : 0;
+    p.touched = ctx->cur_touched;
+    p.tiles_x = (ctx->aoi.xsize + VS_TILE_W - 1) / VS_TILE_W;
     p.w_magic = W > 0 ? (((1ull << 48) + (unsigned long long)W - 1) / (unsigned long long)W) : 0;
 
     VsEllipsoidConsts c = vs_make_ellipsoid_consts();
@@ -492,6 +538,8 @@ int vs_unproject_rasterize(vs_ctx* ctx, const float* depth, int32_t H, int32_t W
 #undef VS_LAUNCH_K1
         VS_CHECK_LAUNCH(ctx, "k_unproject_scatter");
     } else {
+        if (ctx->cur_touched != nullptr)   // exact-chain kernel (polynomial disabled): no per-point marking, every tile counts
+            VS_CUDA(cudaMemsetAsync(ctx->cur_touched, 1, (size_t)p.tiles_x * ((ctx->aoi.ysize + VS_TILE_H - 1) / VS_TILE_H), stream));
         const int grid = persistent_grid(ctx, n_pix, 4);
         k_unproject_scatter_exact<<<grid, kThreads, 0, stream>>>(p, c, ctx->geo, P.center[0], 1.0 / P.inv_half[0],
                                                                 P.center[1], 1.0 / P.inv_half[1], depth, keygrid,

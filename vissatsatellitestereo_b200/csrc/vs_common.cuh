@@ -75,6 +75,7 @@ struct vs_ctx {
     size_t scratch_doubles;
     void* d_exact;  // VsExactParams on the device (geo_chain.cuh)
     bool no_tma;    // true unless VISSAT_TMA=1: stage B uses the plain-load kernels (see api.cu)
+    bool k1_warp_agg; // VISSAT_K1_WARPAGG=1 (read at context creation): warp-aggregated scatter in K1 (A/B variant)
     bool k2_legacy; // VISSAT_K2_LEGACY=1 (read at context creation): round-1 float-space stage B instead of finalize_keys.cu
     // vs_views_to_dsm runs odd and even views on two internal streams (stage A of one view overlaps stage B of the
     // previous one: they are bound by different pipes); the odd views scatter into a second, library-owned key grid
@@ -92,6 +93,11 @@ struct vs_ctx {
     int occ_words;
     const float* occ_stack_base;
     int64_t occ_view0;
+    // sparse mode of vs_views_to_dsm (occupancy bitmap in use): per internal stream a "touched" byte per tile, written
+    // by stage A; stage B and the key-grid clear visit only touched tiles (pipeline.cu)
+    unsigned char* d_touched[VS_MAX_STREAMS];
+    size_t touched_tiles;
+    unsigned char* cur_touched;   // the map of the view being rasterised (nullptr: dense mode)
     // scratch of vs_fuse_views_sparse: per-bin tile lists (fuse.cu)
     int* d_fuse_plan;
     size_t fuse_plan_ints;
