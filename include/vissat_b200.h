@@ -76,8 +76,9 @@ typedef struct vs_fit_info {
 /* Per-call counters written by the rasterisers (device memory, 4 x uint64, zeroed by the call). */
 #define VS_STAT_VALID 0     /* pixels/points with a finite position              (aggregate_2p5d_util.py:92) */
 #define VS_STAT_INGRID 1    /* of those, inside the grid                          (lib/proj_to_grid.py:48)    */
-#define VS_STAT_AMBIGUOUS 2 /* in-grid points whose fractional row/col is within `ambiguity_eps` cells of a cell
-                               edge: their floor() may legitimately differ from the float64 CPU chain         */
+#define VS_STAT_AMBIGUOUS 2 /* points whose polynomial row/col is within `ambiguity_eps` cells of a cell edge.  When
+                               stats are requested they are re-evaluated with the exact chain and scattered from
+                               there; what remains is the float64 chains' own ~1e-9 m noise against the CPU's      */
 #define VS_STAT_EXACT 3     /* points that took the exact per-point chain (outside the fitted altitude range) */
 #define VS_NUM_STATS 4
 

@@ -74,11 +74,11 @@ __device__ __forceinline__ void flush_stats(unsigned long long* stats, unsigned 
     if (threadIdx.x < 4 && s_acc[threadIdx.x]) atomicAdd(&stats[threadIdx.x], (unsigned long long)s_acc[threadIdx.x]);
 }
 
-// Sparse mode: remember that a key landed in this tile.  Plain cached load + conditional store of a constant: a stale
-// 0 only costs a redundant store, and a byte never goes back to 0 while a stage-A kernel runs.
+// Sparse mode: remember that a key landed in this tile: an unconditional byte store of a constant (fire and forget).
+// Testing the mark first was measured and is much slower: the load puts an L1/L2 round trip (174 / 194 us per C3 view
+// against 126 without marking) in front of every chunk of a kernel that is latency-bound already.
 __device__ __forceinline__ void mark_touched(unsigned char* __restrict__ touched, int tiles_x, int ri, int ci) {
-    unsigned char* t = touched + (ri >> 5) * tiles_x + (ci >> 6);
-    if (*t == 0) *t = 1;
+    touched[(ri >> 5) * tiles_x + (ci >> 6)] = 1;
 }
 
 // Rare per-point slow path of K1 (point outside the fitted altitude range): exact chain, kept out of line and
@@ -164,10 +164,12 @@ __device__ __forceinline__ void scatter_chunk_generic(const RasterParams& p, con
                             }
                         }
                         const int ci = __double2int_rd(val[0][0]), ri = __double2int_rd(val[1][0]);
-                        if ((unsigned)ci < (unsigned)p.xsize && (unsigned)ri < (unsigned)p.ysize) {
+                        if (audit && (fabs(val[0][0] - rint(val[0][0])) < p.eps || fabs(val[1][0] - rint(val[1][0])) < p.eps)) {
+                            ++cnt[VS_STAT_AMBIGUOUS];      // re-evaluated with the exact chain (see the main path)
+                            const int r = scatter_exact_point(ex, u[0], v[0], w[0], keygrid, p.touched, p.tiles_x);
+                            cnt[VS_STAT_INGRID] += (r != 0);
+                        } else if ((unsigned)ci < (unsigned)p.xsize && (unsigned)ri < (unsigned)p.ysize) {
                             ++cnt[VS_STAT_INGRID];
-                            if (audit && (fabs(val[0][0] - rint(val[0][0])) < p.eps || fabs(val[1][0] - rint(val[1][0])) < p.eps))
-                                ++cnt[VS_STAT_AMBIGUOUS];
                             atomicMax(keygrid + (ri * p.xsize + ci), vs_key32((float)val[2][0]));
                             if (p.touched != nullptr) mark_touched(p.touched, p.tiles_x, ri, ci);
                         }
@@ -185,15 +187,24 @@ __device__ __forceinline__ void scatter_chunk_generic(const RasterParams& p, con
 }
 
 // K1.  Requires n_pix < 2^32 and W < 2^16 for the multiply-shift row index (checked on the host).
-template <int D, int D64>
+// LEAN: the throughput variant -- no counters, no height map, no tile marking, no warp aggregation; those options cost
+// registers in the streaming loop even when they are switched off at run time (80-register cap, 3 CTAs per SM).
+template <int D, int D64, bool LEAN>
 __global__ void __launch_bounds__(kThreads, D64 == 1 ? 3 : 2)
-k_unproject_scatter(RasterParams p, PolyCoefs pc, const VsExactParams* __restrict__ ex, const float* __restrict__ depth,
-                    uint32_t* __restrict__ keygrid, float* __restrict__ height_map,
-                    unsigned long long* __restrict__ stats) {
+k_unproject_scatter(RasterParams p_in, PolyCoefs pc, const VsExactParams* __restrict__ ex, const float* __restrict__ depth,
+                    uint32_t* __restrict__ keygrid, float* __restrict__ height_map_in,
+                    unsigned long long* __restrict__ stats_in) {
+    RasterParams p = p_in;
+    if (LEAN) {
+        p.touched = nullptr;
+        p.warp_agg = 0;
+    }
+    float* __restrict__ height_map = LEAN ? nullptr : height_map_in;
+    unsigned long long* __restrict__ stats = LEAN ? nullptr : stats_in;
     const int64_t n_pix = (int64_t)p.H * p.W;
     const unsigned n_chunks = (unsigned)((n_pix + PX - 1) / PX);
-    const bool audit = stats != nullptr;
-    const bool want_hm = height_map != nullptr;
+    const bool audit = !LEAN && stats != nullptr;
+    const bool want_hm = !LEAN && height_map != nullptr;
     unsigned cnt[4] = {0, 0, 0, 0};
 
     // Row pitch a multiple of PX (the usual case): no chunk straddles a row and chunk c is the aligned float4 c, so the
@@ -321,12 +332,18 @@ k_unproject_scatter(RasterParams p, PolyCoefs pc, const VsExactParams* __restric
         int cell[PX];
 #pragma unroll
         for (int i = 0; i < PX; ++i) {
+            if (audit && fast[i] && amb[i]) {
+                // Audited mode (stats requested: the drop-in API path): a point whose polynomial row or column is within
+                // eps of a cell edge -- where the polynomial's ~1e-8 cell error could change the floor -- is re-evaluated
+                // with the exact chain and scattered from there (about 4e-7 of the points; the call is out of line).
+                ++cnt[VS_STAT_AMBIGUOUS];
+                const int r = scatter_exact_point(ex, u[i], v[i], w[i], keygrid, p.touched, p.tiles_x);
+                cnt[VS_STAT_INGRID] += (r != 0);
+                fast[i] = false;
+            }
             fast[i] = fast[i] && (unsigned)ci[i] < (unsigned)p.xsize && (unsigned)ri[i] < (unsigned)p.ysize;
             cell[i] = ri[i] * p.xsize + ci[i];
-            if (audit) {
-                cnt[VS_STAT_INGRID] += fast[i];
-                cnt[VS_STAT_AMBIGUOUS] += fast[i] && amb[i];
-            }
+            if (audit) cnt[VS_STAT_INGRID] += fast[i];
         }
         if (p.touched != nullptr) {   // block-uniform: sparse mode
             int prev = -1;
@@ -334,8 +351,7 @@ k_unproject_scatter(RasterParams p, PolyCoefs pc, const VsExactParams* __restric
             for (int i = 0; i < PX; ++i) {
                 const int t = (ri[i] >> 5) * p.tiles_x + (ci[i] >> 6);
                 if (fast[i] && t != prev) {
-                    unsigned char* q = p.touched + t;
-                    if (*q == 0) *q = 1;
+                    p.touched[t] = 1;
                     prev = t;
                 }
             }
@@ -522,8 +538,15 @@ int vs_unproject_rasterize(vs_ctx* ctx, const float* depth, int32_t H, int32_t W
         }();
         const int grid = persistent_grid(ctx, (n_pix + PX - 1) / PX, k1_ctas_env ? k1_ctas_env : (P.d64 == 1 ? 3 : 2));
 #define VS_LAUNCH_K1(DEG, LO) \
-    k_unproject_scatter<DEG, LO><<<grid, kThreads, 0, stream>>>(p, pc, ex, depth, keygrid, height_map, d_stats)
-        switch (P.degree * 3 + P.d64) {
+    k_unproject_scatter<DEG, LO, false><<<grid, kThreads, 0, stream>>>(p, pc, ex, depth, keygrid, height_map, d_stats)
+#define VS_LAUNCH_K1_LEAN(DEG, LO) \
+    k_unproject_scatter<DEG, LO, true><<<grid, kThreads, 0, stream>>>(p, pc, ex, depth, keygrid, height_map, d_stats)
+        // degree 3 (every AOI up to a few km) also exists as a lean variant for the plain throughput call
+        const bool lean = P.degree == 3 && d_stats == nullptr && height_map == nullptr && p.touched == nullptr && !p.warp_agg;
+        switch (lean ? P.d64 : P.degree * 3 + P.d64) {
+            case 0: VS_LAUNCH_K1_LEAN(3, 0); break;
+            case 1: VS_LAUNCH_K1_LEAN(3, 1); break;
+            case 2: VS_LAUNCH_K1_LEAN(3, 2); break;
             case 9: VS_LAUNCH_K1(3, 0); break;
             case 10: VS_LAUNCH_K1(3, 1); break;
             case 11: VS_LAUNCH_K1(3, 2); break;
@@ -536,6 +559,7 @@ int vs_unproject_rasterize(vs_ctx* ctx, const float* depth, int32_t H, int32_t W
             default: vs_set_error("vs_unproject_rasterize: bad polynomial degree"); return VS_ERR_STATE;
         }
 #undef VS_LAUNCH_K1
+#undef VS_LAUNCH_K1_LEAN
         VS_CHECK_LAUNCH(ctx, "k_unproject_scatter");
     } else {
         if (ctx->cur_touched != nullptr)   // exact-chain kernel (polynomial disabled): no per-point marking, every tile counts
