@@ -1,7 +1,9 @@
 """Oracle geodesy: numpy float64 restatement of the third-party chain the reference calls.
 
-TEST INFRASTRUCTURE (see oracle/__init__.py).  Parity for this file is UNPINNED by reference-run
-vectors (pymap3d / pyproj / utm are absent here); it is anchored on published known answers.
+TEST INFRASTRUCTURE (see oracle/__init__.py).  No reference-run vectors exist for this file (pymap3d / pyproj / utm
+are absent here); it is pinned instead to an independent 50-digit evaluation of the same maps
+(tests/golden/make_geodesy_mp.py, tests/test_geodesy_pin.py: <= 5e-9 m over the benchmark AOIs) and anchored on
+published known answers.
 
 Reference call sites being restated:
   * lib/latlonalt_enu_converter.py:36-45  -> pymap3d 1.7.15 geodetic2enu / enu2geodetic

@@ -245,10 +245,21 @@ def test_end_to_end_vs_reference_golden(golden, eng_mod, lanes, case):
     want = golden[case + '_fused']
     fragile = op.fusion_fragility([golden[case + '_per_view'][v] for v in range(V)])
     fragile = cv2.dilate(fragile.astype(np.uint8), np.ones((3, 3), np.uint8)).astype(bool)
+    allow = np.zeros(want.shape, dtype=bool)
     if n_amb == 0:
         assert np.array_equal(np.isnan(got), np.isnan(want))
+    else:
+        # a point within 1e-7 cell of a cell edge may land on either side (the float64 chains differ by ~1e-9 m): the
+        # cells it can reach, through the per-view 3x3 fill + 3x3 blur and the final blur, are set aside -- and counted
+        for v in range(V):
+            m, _ = _ambiguous_cells(depths[v], mats[v], aoi, res, 1e-7)
+            allow |= m
+        allow = cv2.dilate(allow.astype(np.uint8), np.ones((7, 7), np.uint8)).astype(bool)
+        assert allow.sum() <= 121 * n_amb
+        assert np.array_equal(np.isnan(got)[~allow], np.isnan(want)[~allow])
     diff = np.abs(got.astype(np.float64) - want.astype(np.float64))
     diff[np.isnan(diff)] = 0
+    diff[allow] = 0
     bad = diff > HEIGHT_TOL
     # a >1 mm difference is only acceptable where the reference's own strict MAD test sits on a float32 tie
     print('[end-to-end {}] fused cells > {} m: {} of {} (fragile mask: {} cells); ambiguous points: {}'.format(

@@ -104,3 +104,35 @@ def test_pipeline_rejects_out_of_scope_steps(tmp_path):
     assert os.path.exists(os.path.join(config['work_dir'], 'aoi.json'))
     with open(os.path.join(config['work_dir'], 'runtime.txt')) as fp:
         assert 'aggregate_2p5d, skipped' in fp.read()
+
+
+@pytest.mark.parametrize('model', ['perspective', 'pinhole'])
+def test_reparam_depth_matches_reference_files(tmp_path, model):
+    """reparam_depth(sparse_dir, save_dir, camera_model) (reparam_depth.py:69-195): the five files it writes, byte for
+    byte against what the REFERENCE wrote for the same sparse model (tests/golden/make_golden_reparam.py ran
+    /root/reference/reparam_depth.py with the reference's own colmap/read_model.py)."""
+    from vissatsatellitestereo_b200.reparam_depth import reparam_depth
+    base = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reparam', model)
+    reparam_depth(os.path.join(base, 'sparse'), str(tmp_path), camera_model=model)
+    names = ['depth_ranges.txt', 'last_rows.txt', 'raw_depth.txt', 'reference_plane.txt', 'reparam_depth.txt']
+    assert sorted(os.listdir(str(tmp_path))) == names
+    for n in names:
+        with open(os.path.join(base, 'want', n)) as fa, open(os.path.join(str(tmp_path), n)) as fb:
+            assert fa.read() == fb.read(), n
+    # and the matrices derived from last_rows.txt invert back to P4 = [K [R | t]; last_row] (reparam_depth.py:117-141)
+    from vissatsatellitestereo_b200.reparam_depth import read_last_rows
+    rows = read_last_rows(os.path.join(str(tmp_path), 'last_rows.txt'))
+    assert len(rows) == 5 and all(r.shape == (4,) and r[0] == 0 and r[1] == 0 and r[2] > 0 for r in rows.values())
+
+
+def test_read_model_text(tmp_path):
+    from vissatsatellitestereo_b200.colmap.read_model import read_model
+    base = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reparam', 'perspective', 'sparse')
+    cams, imgs, pts = read_model(base, ext='.txt')
+    assert len(cams) == 5 and len(imgs) == 5 and len(pts) == 400
+    assert cams[1].model == 'PERSPECTIVE' and cams[1].params.shape == (5,) and imgs[3].name == '0002.png'
+    assert imgs[1].qvec.shape == (4,) and imgs[1].tvec.shape == (3,) and imgs[1].xys.shape[1] == 2
+    p = pts[7]
+    assert p.xyz.shape == (3,) and p.image_ids.size == p.point2D_idxs.size >= 2
+    with pytest.raises(NotImplementedError):
+        read_model(base, ext='.bin')
