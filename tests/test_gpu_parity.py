@@ -388,15 +388,17 @@ def test_tma_pipeline_variant_is_bit_identical(golden, eng_mod, lanes, monkeypat
 
 
 def test_key_space_stage_b_bit_identical_to_round1_kernel(eng_mod, lanes, monkeypatch):
-    """finalize_keys.cu (default: hole fill + 3x3 median computed on the order-preserving keys) against the round-1
-    float-space kernel (VISSAT_K2_LEGACY=1, itself pinned to cv2 / the reference goldens) on random key grids: all hole
+    """finalize_keys.cu (hole fill + 3x3 median computed on the order-preserving keys; used by the sparse mode) against the
+    round-1 float-space kernel (the dense default, itself pinned to cv2 / the reference goldens) on random key grids: all hole
     densities, NaN regions wider than the fill, odd row pitch, edge tiles, 1-row / 1-column grids."""
     from vissatsatellitestereo_b200 import synthetic as S
     import ctypes as C
     from vissatsatellitestereo_b200._native import lib, check
     cfg = S.scaled(S.CONFIGS['C1'], views=1, depth=64, grid=32)
     aoi = S.make_aoi(cfg, geodesy)
-    new = eng_mod.DsmEngine(aoi, cfg.res, cfg.res, simd_lanes=lanes)
+    monkeypatch.setenv('VISSAT_K2_KEYS', '1')
+    new = eng_mod.DsmEngine(aoi, cfg.res, cfg.res, simd_lanes=lanes)          # the switches are read at context creation
+    monkeypatch.delenv('VISSAT_K2_KEYS')
     monkeypatch.setenv('VISSAT_K2_LEGACY', '1')
     old = eng_mod.DsmEngine(aoi, cfg.res, cfg.res, simd_lanes=lanes)
     monkeypatch.delenv('VISSAT_K2_LEGACY')

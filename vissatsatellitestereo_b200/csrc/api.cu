@@ -168,7 +168,8 @@ int vs_ctx_create(int device, vs_ctx** out) {
         const char* wa = getenv("VISSAT_K1_WARPAGG");
         ctx->k1_warp_agg = wa != nullptr && wa[0] == '1';
         const char* l = getenv("VISSAT_K2_LEGACY");
-        ctx->k2_legacy = l != nullptr && l[0] == '1';
+        const char* kk = getenv("VISSAT_K2_KEYS");
+        ctx->k2_mode = (l != nullptr && l[0] == '1') ? 1 : ((kk != nullptr && kk[0] == '1') ? 2 : 0);
     }
     ctx->ev_used = 0;
     *out = ctx;
@@ -209,6 +210,18 @@ int vs_launch_count(vs_ctx* ctx, uint64_t* out) {
 }
 
 }  // extern "C"
+
+int vs_ensure_side_streams(vs_ctx* ctx, int n) {
+    if (n > VS_MAX_STREAMS) n = VS_MAX_STREAMS;
+    for (int i = 0; i < n; ++i) {
+        if (!ctx->side_stream[i]) {
+            VS_CUDA(cudaStreamCreateWithFlags(&ctx->side_stream[i], cudaStreamNonBlocking));
+            VS_CUDA(cudaEventCreateWithFlags(&ctx->join_event[i], cudaEventDisableTiming));
+        }
+    }
+    if (!ctx->fork_event) VS_CUDA(cudaEventCreateWithFlags(&ctx->fork_event, cudaEventDisableTiming));
+    return VS_OK;
+}
 
 int vs_ensure_scratch(vs_ctx* ctx, size_t doubles) {
     if (ctx->scratch_doubles >= doubles) return VS_OK;

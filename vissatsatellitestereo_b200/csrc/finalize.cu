@@ -316,8 +316,11 @@ k_median3x3(const float* __restrict__ in, int in_row0, int H, int W, int row_beg
 
 }  // namespace
 
-// key-space kernels (finalize_keys.cu): the default float32-key path.  VISSAT_K2_LEGACY=1 selects the round-1 kernels
-// of this file (k_grid_finalize<uint32_t, .>), kept for A/B measurements; both are bit-identical.
+// Two bit-identical implementations of stage B for float32 keys: the float-space kernels of this file
+// (k_grid_finalize<uint32_t, .>, round 1) and the key-space kernels of finalize_keys.cu (round 2).  Measured: equal on
+// C2 views (31.3 vs 31.5 us), the float-space one faster where holes dominate (C5: 137 vs 152 us, C4: 25.3 vs 26.3).
+// So: dense calls use the float-space kernel; the sparse mode (occupancy bitmap / sparse exchange), which needs the
+// touched-tile early-out, uses the key-space one.  VISSAT_K2_LEGACY=1 / VISSAT_K2_KEYS=1 force one of them.
 int vs_launch_finalize_keys(vs_ctx* ctx, const uint32_t* keygrid, int xsize, int ysize, float* dsm_out, int simd_cols,
                             unsigned long long* nan_count, cudaStream_t stream);
 int vs_launch_finalize_keys_occ(vs_ctx* ctx, const uint32_t* keygrid, int xsize, int ysize, float* dsm_out, int simd_cols,
@@ -331,7 +334,7 @@ int vs_launch_finalize_keys_peer(vs_ctx* ctx, const uint32_t* keygrid, int xsize
 int vs_grid_finalize_peer(vs_ctx* ctx, const uint32_t* keygrid, int xsize, int ysize, float* dsm_out, int simd_lanes,
                           uint64_t* nan_count, const VsPeerPlan& plan, cudaStream_t stream) {
     if (nan_count) VS_CUDA(cudaMemsetAsync(nan_count, 0, sizeof(uint64_t), stream));
-    if (!ctx->k2_legacy)
+    if (ctx->k2_mode == 2 || (ctx->k2_mode == 0 && plan.occ_words > 0))     // sparse exchange: key-space kernel
         return vs_launch_finalize_keys_peer(ctx, keygrid, xsize, ysize, dsm_out, simd_cols_for(xsize, simd_lanes),
                                             reinterpret_cast<unsigned long long*>(nan_count), plan, ctx->cur_touched, stream);
     PeerSink sink;
@@ -349,7 +352,7 @@ int vs_grid_finalize_peer(vs_ctx* ctx, const uint32_t* keygrid, int xsize, int y
 int vs_grid_finalize_occ(vs_ctx* ctx, const uint32_t* keygrid, int xsize, int ysize, float* dsm_out, int simd_lanes,
                          uint64_t* nan_count, const VsOccPlan& plan, cudaStream_t stream) {
     if (nan_count) VS_CUDA(cudaMemsetAsync(nan_count, 0, sizeof(uint64_t), stream));
-    if (!ctx->k2_legacy)
+    if (ctx->k2_mode != 1)                                                  // occupancy marking: key-space kernel
         return vs_launch_finalize_keys_occ(ctx, keygrid, xsize, ysize, dsm_out, simd_cols_for(xsize, simd_lanes),
                                            reinterpret_cast<unsigned long long*>(nan_count), plan, ctx->cur_touched, stream);
     OccSink sink;
@@ -385,7 +388,7 @@ int vs_grid_finalize(vs_ctx* ctx, const uint32_t* keygrid, int32_t xsize, int32_
         if (r < 0) return VS_ERR_CUDA;
         if (r > 0) return VS_OK;
     }
-    if (!ctx->k2_legacy)
+    if (ctx->k2_mode == 2)                                                  // dense: the float-space kernel below is the default
         return vs_launch_finalize_keys(ctx, keygrid, xsize, ysize, dsm_out, simd_cols_for(xsize, simd_lanes),
                                        reinterpret_cast<unsigned long long*>(nan_count), stream);
     dim3 grid((xsize + TW - 1) / TW, (ysize + TH - 1) / TH);

@@ -766,21 +766,22 @@ __device__ __forceinline__ void unit_geometry(const SparseGeom& g, int u, int& t
 
 template <int NV>
 __global__ void __launch_bounds__(kBlockSmall, NV <= 32 ? 6 : NV <= 64 ? 5 : NV <= 112 ? 4 : 2)
-k_fuse_sparse_regs(const __grid_constant__ SparseGeom g, int bin) {
+k_fuse_sparse_regs(const __grid_constant__ SparseGeom g, int bin, int sl) {
     __shared__ uint32_t s_bits[kMaxOccWords];
     __shared__ int s_list[NV], s_perm[NV], s_cnt[kMaxGroups];
     __shared__ unsigned short s_gend[kMaxGroups];
     const SumGroups sg{s_perm, s_gend};
-    const int n_items = g.bin_count[bin] * 4;
+    const int n_items = g.bin_count[bin] << sl;      // 2^sl slabs of (32 >> sl) rows per tile
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int u = g.bin_list[(size_t)bin * g.n_units + (item >> 2)];
+        const int u = g.bin_list[(size_t)bin * g.n_units + (item >> sl)];
         int ty, tx;
         unit_geometry(g, u, ty, tx);
         __syncthreads();   // the previous item's readers of the shared lists are done
         const int n = build_view_list(g.occ + ((size_t)ty * g.tiles_x + tx) * g.occ_words, g.occ_words, s_bits, s_list, NV);
         build_sum_groups(g, s_list, n, s_perm, s_gend, s_cnt);
-        const int gy0 = max(ty * VS_TILE_H + (item & 3) * 8, g.row0);
-        const int gy1 = min(min(ty * VS_TILE_H + (item & 3) * 8 + 8, g.row0 + g.rows), (ty + 1) * VS_TILE_H);
+        const int slab = item & ((1 << sl) - 1), slab_rows = VS_TILE_H >> sl;
+        const int gy0 = max(ty * VS_TILE_H + slab * slab_rows, g.row0);
+        const int gy1 = min(min(ty * VS_TILE_H + (slab + 1) * slab_rows, g.row0 + g.rows), (ty + 1) * VS_TILE_H);
         for (int c = threadIdx.x; c < VS_TILE_W * (gy1 - gy0); c += kBlockSmall) {
             const int gy = gy0 + (c >> 6), gx = tx * VS_TILE_W + (c & 63);
             if (gx >= g.W) continue;
@@ -813,23 +814,24 @@ k_fuse_sparse_regs(const __grid_constant__ SparseGeom g, int bin) {
 // More than 128 views in a tile: the multi-lane path of k_fuse_large over the tile's view list.
 template <int LANES, int NVL>
 __global__ void __launch_bounds__(kLargeThreads)
-k_fuse_sparse_large(const __grid_constant__ SparseGeom g, int bin, int VS) {
+k_fuse_sparse_large(const __grid_constant__ SparseGeom g, int bin, int VS, int sl) {
     constexpr int CELLS = kLargeThreads / LANES;   // cells per pass: 64, 32 or 8 consecutive columns of one tile row
     constexpr int PASSES_PER_ROW = VS_TILE_W / CELLS;
     extern __shared__ uint32_t s_tile[];           // CELLS x VS words
     __shared__ uint32_t s_bits[kMaxOccWords];
     __shared__ int s_list[LANES * NVL];
     const int tid = threadIdx.x;
-    const int n_items = g.bin_count[bin] * 4;
+    const int n_items = g.bin_count[bin] << sl;      // 2^sl slabs of (32 >> sl) rows per tile
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int u = g.bin_list[(size_t)bin * g.n_units + (item >> 2)];
+        const int u = g.bin_list[(size_t)bin * g.n_units + (item >> sl)];
         int ty, tx;
         unit_geometry(g, u, ty, tx);
         __syncthreads();
         const int n = build_view_list(g.occ + ((size_t)ty * g.tiles_x + tx) * g.occ_words, g.occ_words, s_bits, s_list,
                                       LANES * NVL);
-        const int gy0 = max(ty * VS_TILE_H + (item & 3) * 8, g.row0);
-        const int gy1 = min(min(ty * VS_TILE_H + (item & 3) * 8 + 8, g.row0 + g.rows), (ty + 1) * VS_TILE_H);
+        const int slab = item & ((1 << sl) - 1), slab_rows = VS_TILE_H >> sl;
+        const int gy0 = max(ty * VS_TILE_H + slab * slab_rows, g.row0);
+        const int gy1 = min(min(ty * VS_TILE_H + (slab + 1) * slab_rows, g.row0 + g.rows), (ty + 1) * VS_TILE_H);
         const BitsPresent present{s_bits};
         for (int pass = 0; pass < (gy1 - gy0) * PASSES_PER_ROW; ++pass) {
             const int gy = gy0 + pass / PASSES_PER_ROW;
@@ -999,22 +1001,23 @@ struct IdentitySlot {
 
 template <int NVL>
 __global__ void __launch_bounds__(kPairThreads, 4)
-k_fuse_sparse_pair(const __grid_constant__ SparseGeom g, int bin) {
+k_fuse_sparse_pair(const __grid_constant__ SparseGeom g, int bin, int sl) {
     __shared__ uint32_t s_bits[kMaxOccWords];
     __shared__ int s_list[2 * NVL], s_perm[2 * NVL], s_cnt[kMaxGroups];
     __shared__ unsigned short s_gend[kMaxGroups];
     const SumGroups sg{s_perm, s_gend};
-    const int n_items = g.bin_count[bin] * 4;
+    const int n_items = g.bin_count[bin] << sl;      // 2^sl slabs of (32 >> sl) rows per tile
     const bool is_b = threadIdx.x & 1;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int u = g.bin_list[(size_t)bin * g.n_units + (item >> 2)];
+        const int u = g.bin_list[(size_t)bin * g.n_units + (item >> sl)];
         int ty, tx;
         unit_geometry(g, u, ty, tx);
         __syncthreads();
         const int n = build_view_list(g.occ + ((size_t)ty * g.tiles_x + tx) * g.occ_words, g.occ_words, s_bits, s_list, 2 * NVL);
         build_sum_groups(g, s_list, n, s_perm, s_gend, s_cnt);
-        const int gy0 = max(ty * VS_TILE_H + (item & 3) * 8, g.row0);
-        const int gy1 = min(min(ty * VS_TILE_H + (item & 3) * 8 + 8, g.row0 + g.rows), (ty + 1) * VS_TILE_H);
+        const int slab = item & ((1 << sl) - 1), slab_rows = VS_TILE_H >> sl;
+        const int gy0 = max(ty * VS_TILE_H + slab * slab_rows, g.row0);
+        const int gy1 = min(min(ty * VS_TILE_H + (slab + 1) * slab_rows, g.row0 + g.rows), (ty + 1) * VS_TILE_H);
         const ListSlot slot{s_list};
         const unsigned pm = 3u << ((threadIdx.x & 31) & ~1);      // the two lanes of this cell
         for (int row = gy0; row < gy1; ++row) {
@@ -1061,8 +1064,8 @@ k_fuse_pair(const __grid_constant__ SparseGeom g, int64_t n_cells) {
 
 template <int NVL>
 int launch_sparse_pair(vs_ctx* ctx, const SparseGeom& g, int bin, cudaStream_t stream) {
-    const int blocks = std::min(g.n_units * 4, ctx->sm_count * 8);
-    k_fuse_sparse_pair<NVL><<<blocks, kPairThreads, 0, stream>>>(g, bin);
+    const int blocks = std::min(g.n_units << 4, ctx->sm_count * 8);
+    k_fuse_sparse_pair<NVL><<<blocks, kPairThreads, 0, stream>>>(g, bin, 4);
     VS_CHECK_LAUNCH(ctx, "k_fuse_sparse_pair");
     return VS_OK;
 }
@@ -1083,11 +1086,14 @@ int launch_pair(vs_ctx* ctx, const float* views, int64_t plane_stride, int V, in
     return VS_OK;
 }
 
+// Work items are slabs of a tile: the more views a bin has, the thinner the slab (an item of a 100-view bin is ~50 KB of
+// loads per row), so that the persistent grid of every bin ends on a short tail.
 template <int NV>
 int launch_sparse_regs(vs_ctx* ctx, const SparseGeom& g, int bin, cudaStream_t stream) {
     // persistent grid: the number of tiles of this bin is only known on the device
-    const int blocks = std::min(g.n_units * 4, ctx->sm_count * 8);
-    k_fuse_sparse_regs<NV><<<blocks, kBlockSmall, 0, stream>>>(g, bin);
+    constexpr int sl = NV <= 32 ? 2 : NV <= 64 ? 3 : 4;
+    const int blocks = std::min(g.n_units << sl, ctx->sm_count * 8);
+    k_fuse_sparse_regs<NV><<<blocks, kBlockSmall, 0, stream>>>(g, bin, sl);
     VS_CHECK_LAUNCH(ctx, "k_fuse_sparse_regs");
     return VS_OK;
 }
@@ -1099,8 +1105,8 @@ int launch_sparse_large(vs_ctx* ctx, const SparseGeom& g, int bin, cudaStream_t 
     VS += (9 - (VS & 31) + 32) & 31;
     const size_t smem = (size_t)CELLS * VS * sizeof(uint32_t);
     VS_CUDA(cudaFuncSetAttribute(k_fuse_sparse_large<LANES, NVL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int blocks = std::min(g.n_units * 4, ctx->sm_count * 4);
-    k_fuse_sparse_large<LANES, NVL><<<blocks, kLargeThreads, smem, stream>>>(g, bin, VS);
+    const int blocks = std::min(g.n_units << 4, ctx->sm_count * 4);
+    k_fuse_sparse_large<LANES, NVL><<<blocks, kLargeThreads, smem, stream>>>(g, bin, VS, 4);
     VS_CHECK_LAUNCH(ctx, "k_fuse_sparse_large");
     return VS_OK;
 }
@@ -1253,10 +1259,24 @@ extern "C" int vs_fuse_views_sparse(vs_ctx* ctx, const float* views, int64_t pla
     k_fuse_plan<<<(g.n_units + 255) / 256, 256, 0, stream>>>(occ, occ_words, g.tiles_x, g.ty_first, g.n_units, bin_count,
                                                              bin_list);
     VS_CHECK_LAUNCH(ctx, "k_fuse_plan");
-    // one launch per bin that this view count can reach (a tile never has more than n_views views)
-    int rc = VS_OK;
-    for (int b = 0; b < kSparseBins && rc == VS_OK; ++b) {
-        if (b > 0 && h_bin_cap[b - 1] >= n_views) break;
+    // One launch per bin that this view count can reach (a tile never has more than n_views views).  The bins work on
+    // disjoint tiles, so they are spread over the caller's stream and two internal ones: the tail of one bin's
+    // persistent grid overlaps the start of the next (fork / join with events, legal inside a stream capture).
+    constexpr int kFuseStreams = 3;
+    cudaStream_t lanes[kFuseStreams] = {stream, stream, stream};
+    bool forked = false;
+    if (vs_ensure_side_streams(ctx, kFuseStreams - 1) == VS_OK) {
+        VS_CUDA(cudaEventRecord(ctx->fork_event, stream));
+        for (int i = 1; i < kFuseStreams; ++i) {
+            VS_CUDA(cudaStreamWaitEvent(ctx->side_stream[i - 1], ctx->fork_event, 0));
+            lanes[i] = ctx->side_stream[i - 1];
+        }
+        forked = true;
+    }
+    int rc = VS_OK, n_launch = 0;
+    for (int b = kSparseBins - 1; b >= 0 && rc == VS_OK; --b) {      // heaviest bins first
+        if (b > 0 && h_bin_cap[b - 1] >= n_views) continue;
+        cudaStream_t stream = lanes[n_launch++ % kFuseStreams];     // shadows the caller's stream for this launch
         switch (b) {
             case 0: rc = launch_sparse_regs<8>(ctx, g, b, stream); break;
             case 1: rc = launch_sparse_regs<16>(ctx, g, b, stream); break;
@@ -1277,6 +1297,14 @@ extern "C" int vs_fuse_views_sparse(vs_ctx* ctx, const float* views, int64_t pla
             case 16: rc = launch_sparse_large<8, 64>(ctx, g, b, stream); break;
             case 17: rc = launch_sparse_large<32, 32>(ctx, g, b, stream); break;
             case 18: rc = launch_sparse_large<32, 64>(ctx, g, b, stream); break;
+        }
+    }
+    if (forked) {   // join even after an error: the caller's stream stays ordered after everything enqueued here
+        for (int i = 1; i < kFuseStreams; ++i) {
+            if (cudaEventRecord(ctx->join_event[i - 1], ctx->side_stream[i - 1]) != cudaSuccess ||
+                cudaStreamWaitEvent(lanes[0], ctx->join_event[i - 1], 0) != cudaSuccess) {
+                if (rc == VS_OK) rc = vs_cuda_fail(cudaGetLastError(), "vs_fuse_views_sparse: join");
+            }
         }
     }
     return rc;

@@ -62,7 +62,7 @@ int vs_views_to_dsm(vs_ctx* ctx, int32_t n_views, const float* const* depth, con
     // Sparse mode (an occupancy bitmap is being written: large AOIs where a view covers part of the grid): stage A marks
     // the tiles it puts keys into, stage B looks only at tiles with a marked neighbour, and the key grid is cleared
     // tile by tile after stage B instead of by a whole-grid memset per view.  The key grids are zeroed once per call.
-    const bool sparse = !ctx->k2_legacy && ctx->poly.degree > 0 &&
+    const bool sparse = ctx->k2_mode != 1 && ctx->poly.degree > 0 &&
                         (ctx->xch_on ? ctx->xch.occ_words > 0 : ctx->occ != nullptr);
     const size_t n_tiles = (size_t)((xs + VS_TILE_W - 1) / VS_TILE_W) * ((ys + VS_TILE_H - 1) / VS_TILE_H);
     if (sparse) {

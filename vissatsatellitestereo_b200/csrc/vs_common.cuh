@@ -76,7 +76,8 @@ struct vs_ctx {
     void* d_exact;  // VsExactParams on the device (geo_chain.cuh)
     bool no_tma;    // true unless VISSAT_TMA=1: stage B uses the plain-load kernels (see api.cu)
     bool k1_warp_agg; // VISSAT_K1_WARPAGG=1 (read at context creation): warp-aggregated scatter in K1 (A/B variant)
-    bool k2_legacy; // VISSAT_K2_LEGACY=1 (read at context creation): round-1 float-space stage B instead of finalize_keys.cu
+    int k2_mode;    // stage-B kernel choice, read at context creation: 0 = auto (float-space kernel for dense calls, key-space
+                    // kernel for the sparse mode), 1 = VISSAT_K2_LEGACY=1 (float-space everywhere), 2 = VISSAT_K2_KEYS=1
     // vs_views_to_dsm runs odd and even views on two internal streams (stage A of one view overlaps stage B of the
     // previous one: they are bound by different pipes); the odd views scatter into a second, library-owned key grid
     cudaStream_t side_stream[VS_MAX_STREAMS];
@@ -171,5 +172,6 @@ __device__ __forceinline__ double vs_unkey64(unsigned long long k) {
 }
 
 // host-side helpers implemented in api.cu
+int vs_ensure_side_streams(vs_ctx* ctx, int n);   // side_stream[0..n), join_event[0..n), fork_event
 int vs_ensure_scratch(vs_ctx* ctx, size_t doubles);
 int vs_upload_exact_params(vs_ctx* ctx);  // aoi_fit.cu
