@@ -1064,8 +1064,8 @@ k_fuse_pair(const __grid_constant__ SparseGeom g, int64_t n_cells) {
 
 template <int NVL>
 int launch_sparse_pair(vs_ctx* ctx, const SparseGeom& g, int bin, cudaStream_t stream) {
-    const int blocks = std::min(g.n_units << 4, ctx->sm_count * 8);
-    k_fuse_sparse_pair<NVL><<<blocks, kPairThreads, 0, stream>>>(g, bin, 4);
+    const int blocks = std::min(g.n_units << 2, ctx->sm_count * 8);
+    k_fuse_sparse_pair<NVL><<<blocks, kPairThreads, 0, stream>>>(g, bin, 2);
     VS_CHECK_LAUNCH(ctx, "k_fuse_sparse_pair");
     return VS_OK;
 }
@@ -1086,12 +1086,13 @@ int launch_pair(vs_ctx* ctx, const float* views, int64_t plane_stride, int V, in
     return VS_OK;
 }
 
-// Work items are slabs of a tile: the more views a bin has, the thinner the slab (an item of a 100-view bin is ~50 KB of
-// loads per row), so that the persistent grid of every bin ends on a short tail.
+// Work items are slabs of a tile: 2^sl slabs of (32 >> sl) rows.  Measured on C3 (200 views, 8192^2 cells): 4 slabs of 8
+// rows for every bin 34.6 ms; thinner slabs for the bins with many views (8 / 16 per tile) plus the bins spread over three
+// streams 36.2 ms -- the per-item list building costs more than the shorter tails save.
 template <int NV>
 int launch_sparse_regs(vs_ctx* ctx, const SparseGeom& g, int bin, cudaStream_t stream) {
     // persistent grid: the number of tiles of this bin is only known on the device
-    constexpr int sl = NV <= 32 ? 2 : NV <= 64 ? 3 : 4;
+    constexpr int sl = 2;
     const int blocks = std::min(g.n_units << sl, ctx->sm_count * 8);
     k_fuse_sparse_regs<NV><<<blocks, kBlockSmall, 0, stream>>>(g, bin, sl);
     VS_CHECK_LAUNCH(ctx, "k_fuse_sparse_regs");
@@ -1105,8 +1106,8 @@ int launch_sparse_large(vs_ctx* ctx, const SparseGeom& g, int bin, cudaStream_t 
     VS += (9 - (VS & 31) + 32) & 31;
     const size_t smem = (size_t)CELLS * VS * sizeof(uint32_t);
     VS_CUDA(cudaFuncSetAttribute(k_fuse_sparse_large<LANES, NVL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int blocks = std::min(g.n_units << 4, ctx->sm_count * 4);
-    k_fuse_sparse_large<LANES, NVL><<<blocks, kLargeThreads, smem, stream>>>(g, bin, VS, 4);
+    const int blocks = std::min(g.n_units << 2, ctx->sm_count * 4);
+    k_fuse_sparse_large<LANES, NVL><<<blocks, kLargeThreads, smem, stream>>>(g, bin, VS, 2);
     VS_CHECK_LAUNCH(ctx, "k_fuse_sparse_large");
     return VS_OK;
 }
@@ -1259,24 +1260,10 @@ extern "C" int vs_fuse_views_sparse(vs_ctx* ctx, const float* views, int64_t pla
     k_fuse_plan<<<(g.n_units + 255) / 256, 256, 0, stream>>>(occ, occ_words, g.tiles_x, g.ty_first, g.n_units, bin_count,
                                                              bin_list);
     VS_CHECK_LAUNCH(ctx, "k_fuse_plan");
-    // One launch per bin that this view count can reach (a tile never has more than n_views views).  The bins work on
-    // disjoint tiles, so they are spread over the caller's stream and two internal ones: the tail of one bin's
-    // persistent grid overlaps the start of the next (fork / join with events, legal inside a stream capture).
-    constexpr int kFuseStreams = 3;
-    cudaStream_t lanes[kFuseStreams] = {stream, stream, stream};
-    bool forked = false;
-    if (vs_ensure_side_streams(ctx, kFuseStreams - 1) == VS_OK) {
-        VS_CUDA(cudaEventRecord(ctx->fork_event, stream));
-        for (int i = 1; i < kFuseStreams; ++i) {
-            VS_CUDA(cudaStreamWaitEvent(ctx->side_stream[i - 1], ctx->fork_event, 0));
-            lanes[i] = ctx->side_stream[i - 1];
-        }
-        forked = true;
-    }
-    int rc = VS_OK, n_launch = 0;
-    for (int b = kSparseBins - 1; b >= 0 && rc == VS_OK; --b) {      // heaviest bins first
-        if (b > 0 && h_bin_cap[b - 1] >= n_views) continue;
-        cudaStream_t stream = lanes[n_launch++ % kFuseStreams];     // shadows the caller's stream for this launch
+    // one launch per bin that this view count can reach (a tile never has more than n_views views), on the caller's stream
+    int rc = VS_OK;
+    for (int b = 0; b < kSparseBins && rc == VS_OK; ++b) {
+        if (b > 0 && h_bin_cap[b - 1] >= n_views) break;
         switch (b) {
             case 0: rc = launch_sparse_regs<8>(ctx, g, b, stream); break;
             case 1: rc = launch_sparse_regs<16>(ctx, g, b, stream); break;
@@ -1297,14 +1284,6 @@ extern "C" int vs_fuse_views_sparse(vs_ctx* ctx, const float* views, int64_t pla
             case 16: rc = launch_sparse_large<8, 64>(ctx, g, b, stream); break;
             case 17: rc = launch_sparse_large<32, 32>(ctx, g, b, stream); break;
             case 18: rc = launch_sparse_large<32, 64>(ctx, g, b, stream); break;
-        }
-    }
-    if (forked) {   // join even after an error: the caller's stream stays ordered after everything enqueued here
-        for (int i = 1; i < kFuseStreams; ++i) {
-            if (cudaEventRecord(ctx->join_event[i - 1], ctx->side_stream[i - 1]) != cudaSuccess ||
-                cudaStreamWaitEvent(lanes[0], ctx->join_event[i - 1], 0) != cudaSuccess) {
-                if (rc == VS_OK) rc = vs_cuda_fail(cudaGetLastError(), "vs_fuse_views_sparse: join");
-            }
         }
     }
     return rc;
