@@ -602,7 +602,7 @@ def run_b200_arm(args, cfg):
     if rank == 0:
         sampler.start()
     head = measure(cfg, V * world, (rank * V, (rank + 1) * V), world, rank, dev, args.steps, args.warmup,
-                   sparse=cfg.random_offsets, want_e2e=True, want_graph=True, label=cfg.name)
+                   sparse=cfg.random_offsets, want_e2e=not args.no_e2e, want_graph=True, label=cfg.name)
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- second record: BASELINE.json configs[2] (C3, the config north_star names for the all-to-all), STRONG scaling:
@@ -728,6 +728,7 @@ def main():
     ap.add_argument('--config', default='C2')
     ap.add_argument('--views', type=int, default=None, help='override views per GPU (debugging)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true', help='skip the host-buffer end-to-end leg (kernel experiments)')
     ap.add_argument('--no-c3', action='store_true', help='skip the C3 (strong-scaling, sparse exchange) sub-record')
     args = ap.parse_args()
     from vissatsatellitestereo_b200 import synthetic as S

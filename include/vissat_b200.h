@@ -31,7 +31,7 @@ extern "C" {
 #define VS_ERR_STATE 3   /* call order (e.g. rasterize before vs_set_aoi) */
 #define VS_ERR_FIT 4     /* AOI polynomial could not be validated; exact mode is still available */
 
-#define VS_ABI_VERSION 2
+#define VS_ABI_VERSION 3
 
 typedef struct vs_ctx vs_ctx;
 
@@ -157,6 +157,13 @@ int vs_views_to_dsm(vs_ctx* ctx, int32_t n_views, const float* const* depth, con
 /* Number of internal streams vs_views_to_dsm spreads consecutive views over (1..4, default 4 or $VISSAT_STREAMS).
  * With more than one, stage A of one view overlaps stage B of another (they are bound by different pipes). */
 int vs_set_streams(vs_ctx* ctx, int n_streams);
+
+/* Co-scheduled stages A+B (default on, or $VISSAT_AB=0): vs_views_to_dsm launches ONE kernel per view step whose CTAs
+ * alternate between stage B of the previous view (lib/proj_to_grid.py:62-79 + produce_dsm.py:58) and stage A of the next
+ * (aggregate_2p5d_util.py:75-98 + lib/proj_to_grid.py:42-61), so both instruction mixes share every SM.  Taken when the
+ * call asks for no per-view counters and the AOI polynomial has degree 3; bit-identical to the separate kernels, which
+ * enable = 0 forces (e.g. to time stage A and stage B on their own). */
+int vs_set_coschedule(vs_ctx* ctx, int enable);
 
 /* Per-kernel device timing of vs_views_to_dsm (CUDA events recorded on the launching stream around stage A and stage
  * B of every view).  vs_set_timing(ctx, 1) enables it and resets the log; vs_get_timing synchronises the events and

@@ -143,18 +143,34 @@ def _run_config(name, bands, lanes, views=None, per_view_only=False, check_views
     if also_sparse:
         # the sparse path (stage A marks touched tiles, stage B / the key-grid clear / the fusion visit only those) must
         # give the same per-view planes and the same fused DSM, bit for bit, at the config's full size
+        # -- in BOTH call modes: audited (per-view counters requested, the drop-in API's mode: points within eps of a cell
+        # edge are re-evaluated with the exact chain) and plain (the throughput call).  The two modes may differ from
+        # each other in the few cells such a point can reach, so each is compared with the dense pass of its own mode.
         occ = eng.alloc_occupancy(V)
-        eng.set_occupancy(occ, stack, 0)
-        keep = fused.clone()
-        stack.fill_(-7.0)
-        for rep in range(2):                       # twice: the tile-wise key-grid clear must leave the grids empty
-            occ.zero_()
-            eng.views_to_dsm(depths, mats, stack)
-        eng.set_occupancy(None)
-        fused_sparse = eng.median3x3(eng.fuse(stack, occ=occ), count_nan=True)
-        assert torch.equal(torch.nan_to_num(fused_sparse, nan=-1e9), torch.nan_to_num(keep, nan=-1e9)), \
-            '{}: sparse path differs from the dense path'.format(name)
-        print('[{}] sparse path: bit-identical to the dense path; tile occupancy {:.3f}'.format(
+
+        def n_diff(a, b):
+            return int((torch.nan_to_num(a, nan=-1e9) != torch.nan_to_num(b, nan=-1e9)).sum())
+
+        for mode in ('audited', 'plain'):
+            if mode == 'audited':
+                keep = fused.clone()
+            else:
+                eng.views_to_dsm(depths, mats, stack)
+                keep = eng.fuse_and_blur(stack)
+                print('[{}] audited vs plain dense pass: {} fused cells differ'.format(name, n_diff(keep, fused)))
+            eng.set_occupancy(occ, stack, 0)
+            stack.fill_(-7.0)
+            stats2 = torch.zeros_like(stats)
+            for rep in range(2):                   # twice: the tile-wise key-grid clear must leave the grids empty
+                occ.zero_()
+                eng.views_to_dsm(depths, mats, stack, stats=stats2 if mode == 'audited' else None)
+            eng.set_occupancy(None)
+            fused_sparse = eng.median3x3(eng.fuse(stack, occ=occ), count_nan=True)
+            nd = n_diff(fused_sparse, keep)
+            assert nd == 0, '{}: sparse path differs from the dense path in {} fused cells ({} mode)'.format(name, nd, mode)
+            if mode == 'audited':
+                assert torch.equal(stats2, stats), '{}: K1 counters differ between the sparse and the dense pass'.format(name)
+        print('[{}] sparse path: bit-identical to the dense path (audited and plain calls); tile occupancy {:.3f}'.format(
             name, float(_occupancy_fraction(occ, V))))
         del occ, keep, fused_sparse
 

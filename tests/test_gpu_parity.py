@@ -428,3 +428,55 @@ def test_key_space_stage_b_bit_identical_to_round1_kernel(eng_mod, lanes, monkey
             assert na == no == int(np.isnan(a).sum())
     new.close()
     old.close()
+
+
+@pytest.mark.parametrize('case', [dict(views=7, depth=256, grid=160), dict(views=1, depth=128, grid=64),
+                                  dict(views=5, depth=(130, 203), grid=97), dict(views=9, depth=512, grid=300)])
+def test_coscheduled_stage_ab_bit_identical_to_separate_kernels(eng_mod, lanes, case):
+    """stage_ab.cu (one kernel per view step: stage B of the previous view + stage A of the next + the key-grid clear, work
+    taken from two device queues) against the separate stage-A / stage-B kernels (themselves pinned to the reference goldens):
+    per-view planes, NaN counters and the fused DSM, bit for bit; odd view counts (the views alternate between internal
+    streams), a single view, a depth map whose row pitch is not a multiple of 4 pixels, repeated calls (the three rotating
+    key grids of a stream must come back empty), 1..4 internal streams."""
+    from vissatsatellitestereo_b200 import synthetic as S
+    d = case['depth']
+    cfg = S.scaled(S.CONFIGS['C1'], views=case['views'], depth=d if isinstance(d, int) else d[0], grid=case['grid'])
+    if not isinstance(d, int):
+        cfg.height, cfg.width = d
+    scene = S.make_scene(cfg, geodesy, device='cuda')
+    eng = eng_mod.DsmEngine(scene.aoi, cfg.res, cfg.res, simd_lanes=lanes)
+    assert eng.fit['degree'] == 3
+    V = cfg.n_views
+    depths = list(scene.depths)
+    depths[0] = depths[0].clone()
+    depths[0][::3, 1::4] = float('nan')          # invalid pixels
+    depths[0][5:9, :] = -1.0
+    want = torch.empty((V, eng.n_size, eng.e_size), dtype=torch.float32, device='cuda')
+    want_nan = torch.zeros(V, dtype=torch.int64, device='cuda')
+    eng.set_coschedule(False)
+    eng.views_to_dsm(depths, scene.mats, want, count_nan=want_nan)
+    want_fused = eng.fuse_and_blur(want) if V >= 3 else None
+    eng.set_coschedule(True)
+    n0 = eng.launch_count()
+    for streams in (4, 1, 2, 3):
+        eng.set_streams(streams)
+        for rep in range(2):
+            got = torch.full_like(want, -7.0)
+            got_nan = torch.full_like(want_nan, -1)
+            eng.views_to_dsm(depths, scene.mats, got, count_nan=got_nan)
+            assert torch.equal(torch.nan_to_num(got, nan=-1e9), torch.nan_to_num(want, nan=-1e9)), (streams, rep)
+            assert torch.equal(got_nan, want_nan)
+    # the co-scheduled path was really taken: V + (streams in use) launches per call instead of 2 V (+ memsets)
+    assert eng.launch_count() - n0 == sum(2 * (V + min(s, 2, V)) for s in (4, 1, 2, 3))
+    if want_fused is not None:
+        assert torch.equal(torch.nan_to_num(eng.fuse_and_blur(got), nan=-1e9), torch.nan_to_num(want_fused, nan=-1e9))
+    # a captured step replays it
+    eng.set_streams(4)
+    stack = torch.empty_like(want)
+    g = eng.capture_step(depths, scene.mats, stack, fuse=V >= 3)
+    stack.fill_(3.0)
+    g.replay()
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(torch.nan_to_num(stack, nan=-1e9), torch.nan_to_num(want, nan=-1e9))
+    eng.close()

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, 'libvissat_b200.so')
 
 VS_NUM_STATS = 4
 STAT_VALID, STAT_INGRID, STAT_AMBIGUOUS, STAT_EXACT = 0, 1, 2, 3
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class VisSatError(RuntimeError):
@@ -71,6 +71,7 @@ SIGNATURES = {
     'vs_views_to_dsm': (C.c_int, [_vp, _i32, C.POINTER(_vp), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_dbl), _vp, _vp,
                                   _i64, C.c_int, _vp, _vp, _vp]),
     'vs_set_streams': (C.c_int, [_vp, C.c_int]),
+    'vs_set_coschedule': (C.c_int, [_vp, C.c_int]),
     'vs_set_timing': (C.c_int, [_vp, C.c_int]),
     'vs_get_timing': (C.c_int, [_vp, _i32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(_i32)]),
     'vs_fuse_views': (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),

@@ -154,6 +154,24 @@ int vs_ctx_create(int device, vs_ctx** out) {
     }
     ctx->fork_event = nullptr;
     ctx->keygrid_extra_cells = 0;
+    for (int i = 0; i < VS_MAX_STREAMS; ++i) ctx->d_keygrid_alt[i] = nullptr;
+    ctx->keygrid_alt_cells = 0;
+    {
+        const char* fc = getenv("VISSAT_FOLD_CLEAR");
+        ctx->fold_clear = !(fc != nullptr && atoi(fc) == 0);
+    }
+    for (int i = 0; i < VS_MAX_STREAMS; ++i)
+        for (int k = 0; k < 3; ++k) ctx->d_keygrid_ab[i][k] = nullptr;
+    ctx->keygrid_ab_cells = 0;
+    ctx->d_ab_counters = nullptr;
+    ctx->ab_counters_ints = 0;
+    {
+        const char* ab = getenv("VISSAT_AB");
+        ctx->ab_on = ab != nullptr && atoi(ab) != 0;   // measured slower than the separate kernels: opt-in
+        const char* e = getenv("VISSAT_AB_STREAMS");
+        const int n = e ? atoi(e) : 2;
+        ctx->ab_streams = n < 1 ? 1 : (n > VS_MAX_STREAMS ? VS_MAX_STREAMS : n);
+    }
     {
         const char* e1 = getenv("VISSAT_STREAMS");
         int n = e1 ? atoi(e1) : 4;
@@ -189,8 +207,13 @@ int vs_ctx_destroy(vs_ctx* ctx) {
         if (ctx->side_stream[i]) cudaStreamDestroy(ctx->side_stream[i]);
         if (ctx->join_event[i]) cudaEventDestroy(ctx->join_event[i]);
         if (ctx->d_keygrid_extra[i]) cudaFree(ctx->d_keygrid_extra[i]);
+        if (ctx->d_keygrid_alt[i]) cudaFree(ctx->d_keygrid_alt[i]);
     }
     if (ctx->fork_event) cudaEventDestroy(ctx->fork_event);
+    for (int i = 0; i < VS_MAX_STREAMS; ++i)
+        for (int k = 0; k < 3; ++k)
+            if (ctx->d_keygrid_ab[i][k]) cudaFree(ctx->d_keygrid_ab[i][k]);
+    if (ctx->d_ab_counters) cudaFree(ctx->d_ab_counters);
     delete ctx;
     return VS_OK;
 }

@@ -14,220 +14,36 @@
 // K4  k_median3x3            aggregate_2p5d.py:81 on a row band (halo rows supplied by the caller); same blur.
 #include <stdlib.h>
 
-#include "finalize_common.cuh"
+#include "finalize_tile.cuh"
 
 using namespace vsfin;
 
 namespace {
 
-// all-empty tile: every output is NaN (hole fill and blur of nothing)
-template <typename T, typename Sink>
-__device__ __forceinline__ void write_nan_tile(float* __restrict__ blur_out, T* __restrict__ filled_out, int ty0, int tx0,
-                                               int H, int W, unsigned long long* __restrict__ nan_count,
-                                               const Sink& sink) {
-    unsigned n = 0;
-    for (int i = threadIdx.x; i < TW * TH; i += kThreads) {
-        const int r = i / TW, c = i - r * TW;
-        const int gy = ty0 + r, gx = tx0 + c;
-        if (gy < H && gx < W) {
-            if (blur_out != nullptr) {
-                blur_out[(size_t)gy * W + gx] = CUDART_NAN_F;
-                if (!sink.skips_empty_tiles()) sink.store1(gy, gx, W, CUDART_NAN_F);
-            }
-            if (filled_out != nullptr) filled_out[(size_t)gy * W + gx] = (T)CUDART_NAN;
-            ++n;
-        }
-    }
-    if (blur_out != nullptr) block_count_flush(n, nan_count);
-}
-
 template <typename Key, typename Sink>
 __global__ void __launch_bounds__(kThreads, sizeof(Key) == 4 ? 5 : 1)   // float32 keys: 48 registers, 5 CTAs per SM
 k_grid_finalize(const Key* __restrict__ keygrid, int W, int H, typename KeyTraits<Key>::value_t* __restrict__ filled_out,
                 float* __restrict__ blur_out, int simd_cols, unsigned long long* __restrict__ nan_count,
-                const __grid_constant__ Sink sink) {
-    typedef typename KeyTraits<Key>::value_t T;
-    constexpr bool kSameTile = sizeof(T) == sizeof(float);   // float32 keys: one tile serves fill and blur
-    __shared__ __align__(16) T s_raw[TR * TS];              // decoded keys; holes are patched in place after phase 2
-    __shared__ __align__(16) float s_fill32[kSameTile ? 4 : TR * TS];  // float32 copy for the f64 path
-    __shared__ unsigned short s_hole_pos[MAX_HOLES];
-    __shared__ float s_hole_val[kSameTile ? MAX_HOLES : 1];
-    __shared__ int s_has_nan;
-    float* s_fill = kSameTile ? reinterpret_cast<float*>(s_raw) : s_fill32;
-    const int tid = threadIdx.x;
-    const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH;
-    if (tid == 0) s_has_nan = 0;
-    __syncthreads();
-
-    // 1. decode keys (+2 halo).  Key 0 (= empty, also used outside the grid) decodes to NaN, and the fill only
-    //    uses in-range neighbours (:73).  Holes = empty cells inside the grid within the 1-cell halo; they are
-    //    appended to a list with one shared atomic per warp-row (ballot-aggregated).
-    //    Warp w loads tile rows w, w+8, ...; lane l takes columns l, l+32 and (l < 4) l+64: no div/mod, and the
-    //    row address is computed once per row.
-    const int warp = tid >> 5, lane = tid & 31;
-    int wcnt = 0;   // holes listed by this warp (warp-uniform)
-    // Interior tiles of a grid whose rows are 16-byte multiples: the 36 x 72 box (grid columns tx0-4 .. tx0+67) is
-    // fetched with 16-byte loads, 18 per row.  Edge tiles (and odd pitches) take the scalar, bounds-checked loader.
-    const bool vec_ok = sizeof(Key) == 4 && (W & 3) == 0 && ((reinterpret_cast<uintptr_t>(keygrid) & 15) == 0) &&
-                        tx0 >= 4 && tx0 + TW + 4 <= W && ty0 >= 2 && ty0 + TH + 2 <= H;
-    if (vec_ok) {
-        constexpr int VPR = TS / 4;                 // 18 vectors per row
-        constexpr int NV4 = (TR * VPR + kThreads - 1) / kThreads;   // 3 per thread
-        uint4 kv[NV4];
-#pragma unroll
-        for (int q = 0; q < NV4; ++q) {             // all loads first
-            const int i = tid + q * kThreads;
-            const int r = i / VPR, v4 = i - r * VPR;
-            kv[q] = make_uint4(0u, 0u, 0u, 0u);
-            if (i < TR * VPR)
-                kv[q] = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint32_t*>(keygrid) +
-                                                       (size_t)(ty0 - 2 + r) * W + (tx0 - 4) + 4 * v4);
-        }
-        {   // a tile whose whole box is empty (large AOIs: most tiles of most views) is all-NaN: skip the work
-            unsigned nz = 0;
-#pragma unroll
-            for (int q = 0; q < NV4; ++q) nz |= kv[q].x | kv[q].y | kv[q].z | kv[q].w;
-            if (!__syncthreads_or(nz != 0)) {
-                write_nan_tile(blur_out, filled_out, ty0, tx0, H, W, nan_count, sink);
-                return;
+                const __grid_constant__ Sink sink, Key* __restrict__ clear_other) {
+    // vs_views_to_dsm alternates between two key grids per internal stream: while this launch consumes one, every CTA
+    // zeroes its own 64x32 tile of the OTHER one (consumed by the previous launch of the stream, scattered into by the
+    // next stage A), which replaces the whole-grid memset per view.  Tiles partition the grid, so no halo is involved.
+    if (clear_other != nullptr) {
+        const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH;
+        if (sizeof(Key) == 4 && (W & 3) == 0 && (reinterpret_cast<uintptr_t>(clear_other) & 15) == 0 && tx0 + TW <= W) {
+            for (int i = threadIdx.x; i < TH * (TW / 4); i += kThreads) {
+                const int r = i / (TW / 4), c4 = i - r * (TW / 4);
+                if (ty0 + r < H)
+                    *reinterpret_cast<uint4*>(clear_other + (size_t)(ty0 + r) * W + tx0 + 4 * c4) = make_uint4(0u, 0u, 0u, 0u);
             }
-        }
-#pragma unroll
-        for (int q = 0; q < NV4; ++q) {
-            const int i = tid + q * kThreads;
-            const int r = i / VPR, v4 = i - r * VPR;
-            const bool act = i < TR * VPR;
-            const uint32_t kk[4] = {kv[q].x, kv[q].y, kv[q].z, kv[q].w};
-            const int pos0 = r * TS + 4 * v4;       // box column 4*v4 <-> tile column 4*v4 - OFF
-            if (act) {
-                float4 f = make_float4(vs_unkey32(kk[0]), vs_unkey32(kk[1]), vs_unkey32(kk[2]), vs_unkey32(kk[3]));
-                *reinterpret_cast<float4*>(reinterpret_cast<float*>(s_raw) + pos0) = f;
-            }
-            const bool row_in = act && (unsigned)(r - 1) < (unsigned)(TH + 2);
-            bool h4[4];
-            bool any_h = false;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int c = 4 * v4 + e - OFF;     // tile column
-                h4[e] = row_in && kk[e] == 0 && (unsigned)(c - 1) < (unsigned)(TW + 2);
-                any_h |= h4[e];
-            }
-            if (__any_sync(0xffffffffu, any_h)) {   // warp-uniform
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const unsigned m = __ballot_sync(0xffffffffu, h4[e]);
-                    if (h4[e]) s_hole_pos[warp * HSEG2 + wcnt + __popc(m & ((1u << lane) - 1u))] = (unsigned short)(pos0 + e);
-                    wcnt += __popc(m);
-                }
-            }
-        }
-    } else {
-        constexpr int NIT = (TR + 7) / 8;   // rows per warp
-        // 1a. issue every global load of this thread before touching the results (memory-level parallelism: the
-        //     phase is latency-bound otherwise)
-        Key keys[NIT][3];
-#pragma unroll
-        for (int it = 0; it < NIT; ++it) {
-            const int r = warp + 8 * it;
-            const int gy = ty0 - 2 + r;
-            const bool row_ok = r < TR && (unsigned)gy < (unsigned)H;
-            const Key* __restrict__ row = keygrid + (size_t)(row_ok ? gy : 0) * W + (tx0 - 2);
-#pragma unroll
-            for (int part = 0; part < 3; ++part) {
-                const int c = lane + 32 * part;
-                const int gx = tx0 - 2 + c;
-                Key key = 0;
-                if (row_ok && (part < 2 || lane < TC - 64) && (unsigned)gx < (unsigned)W) key = row[c];
-                keys[it][part] = key;
-            }
-        }
-        {
-            bool nz = false;
-#pragma unroll
-            for (int it = 0; it < NIT; ++it)
-#pragma unroll
-                for (int part = 0; part < 3; ++part) nz |= (keys[it][part] != 0);
-            if (!__syncthreads_or(nz)) {
-                write_nan_tile(blur_out, filled_out, ty0, tx0, H, W, nan_count, sink);
-                return;
-            }
-        }
-        // 1b. decode, store, list holes.  Every warp keeps its own hole list (count in a register, no atomics).
-#pragma unroll
-        for (int it = 0; it < NIT; ++it) {
-            const int r = warp + 8 * it;
-            if (r < TR) {   // warp-uniform
-                const int gy = ty0 - 2 + r;
-                const bool row_in = (unsigned)gy < (unsigned)H && (unsigned)(r - 1) < (unsigned)(TH + 2);
-#pragma unroll
-                for (int part = 0; part < 3; ++part) {
-                    const int c = lane + 32 * part;
-                    const int pos = r * TS + OFF + c;
-                    bool hole = false;
-                    if (part < 2 || lane < TC - 64) {
-                        const Key key = keys[it][part];
-                        const T v = KeyTraits<Key>::decode(key);
-                        s_raw[pos] = v;
-                        if (!kSameTile) s_fill[pos] = (float)v;     // produce_dsm.py:58 astype(np.float32)
-                        const int gx = tx0 - 2 + c;
-                        hole = key == 0 && row_in && (unsigned)gx < (unsigned)W && (unsigned)(c - 1) < (unsigned)(TW + 2);
-                    }
-                    const unsigned m = __ballot_sync(0xffffffffu, hole);
-                    if (m) {   // warp-uniform
-                        if (hole) s_hole_pos[warp * HSEG2 + wcnt + __popc(m & ((1u << lane) - 1u))] = (unsigned short)pos;
-                        wcnt += __popc(m);
-                    }
-                }
+        } else {
+            for (int i = threadIdx.x; i < TH * TW; i += kThreads) {
+                const int r = i / TW, c = i - r * TW;
+                if (ty0 + r < H && tx0 + c < W) clear_other[(size_t)(ty0 + r) * W + tx0 + c] = 0;
             }
         }
     }
-    if (tid == 0 && blur_out != nullptr) sink.mark_tile(blockIdx.x, blockIdx.y, H);   // this (tile, view) holds data
-    __syncthreads();
-
-    // 2. hole fill: NaN cell <- median of its non-NaN 3x3 neighbours in the PRE-fill grid, dense over the list.
-    //    The fill must not cascade (lib/proj_to_grid.py:65 reads a copy): with one shared tile the results are
-    //    staged and patched in after a barrier; the float64 path reads s_raw and writes the separate float32 tile.
-    {
-        bool nan_left = false;
-        for (int i = lane; i < wcnt; i += 32) {
-            const int pos = s_hole_pos[warp * HSEG2 + i];
-            const T* c = s_raw + pos;
-            T nb[8] = {c[-TS - 1], c[-TS], c[-TS + 1], c[-1], c[1], c[TS - 1], c[TS], c[TS + 1]};
-            const T v = vs_median_of_valid8<T>(nb);
-            nan_left |= (v != v);
-            if (kSameTile) {
-                s_hole_val[warp * HSEG2 + i] = (float)v;
-            } else {
-                s_fill[pos] = (float)v;
-                if (filled_out != nullptr) {
-                    const int r = pos / TS, cc = pos - r * TS - OFF;
-                    const int gy = ty0 - 2 + r, gx = tx0 - 2 + cc;
-                    if (r >= 2 && r < TH + 2 && cc >= 2 && cc < TW + 2) filled_out[(size_t)gy * W + gx] = v;
-                }
-            }
-        }
-        if (nan_left) s_has_nan = 1;
-        __syncthreads();
-        if (kSameTile) {
-            for (int i = lane; i < wcnt; i += 32) s_fill[s_hole_pos[warp * HSEG2 + i]] = s_hole_val[warp * HSEG2 + i];
-            __syncthreads();
-        }
-    }
-    if (filled_out != nullptr) {
-        for (int i = tid; i < TW * TH; i += kThreads) {
-            const int r = i / TW, c = i - r * TW;
-            const int gy = ty0 + r, gx = tx0 + c;
-            const T v = s_raw[(r + 2) * TS + OFF + c + 2];
-            if (gy < H && gx < W && (kSameTile || v == v)) filled_out[(size_t)gy * W + gx] = v;
-        }
-    }
-    if (blur_out == nullptr) return;
-
-    // 3. cv2.medianBlur(., 3) with replicated borders
-    replicate_border(s_fill, ty0, tx0, H, W);
-    __syncthreads();
-    const unsigned n_nan = blur_tile(s_fill, ty0, tx0, H, W, H, s_has_nan != 0, simd_cols != 0, blur_out, 0, sink);
-    block_count_flush(n_nan, nan_count);
+    grid_finalize_tile<Key, Sink>(blockIdx.x, blockIdx.y, keygrid, W, H, filled_out, blur_out, simd_cols, nan_count, sink);
 }
 
 // in: rows [in_row0, ...) of an H_total-row image; writes rows [row_begin, row_end)
@@ -332,7 +148,7 @@ int vs_launch_finalize_keys_peer(vs_ctx* ctx, const uint32_t* keygrid, int xsize
 
 // Stage B of one view with the peer stores of the multi-GPU exchange (called by vs_views_to_dsm, pipeline.cu).
 int vs_grid_finalize_peer(vs_ctx* ctx, const uint32_t* keygrid, int xsize, int ysize, float* dsm_out, int simd_lanes,
-                          uint64_t* nan_count, const VsPeerPlan& plan, cudaStream_t stream) {
+                          uint64_t* nan_count, const VsPeerPlan& plan, cudaStream_t stream, uint32_t* clear_other) {
     if (nan_count) VS_CUDA(cudaMemsetAsync(nan_count, 0, sizeof(uint64_t), stream));
     if (ctx->k2_mode == 2 || (ctx->k2_mode == 0 && plan.occ_words > 0))     // sparse exchange: key-space kernel
         return vs_launch_finalize_keys_peer(ctx, keygrid, xsize, ysize, dsm_out, simd_cols_for(xsize, simd_lanes),
@@ -343,7 +159,7 @@ int vs_grid_finalize_peer(vs_ctx* ctx, const uint32_t* keygrid, int xsize, int y
     k_grid_finalize<uint32_t, PeerSink><<<grid, kThreads, 0, stream>>>(keygrid, xsize, ysize, nullptr, dsm_out,
                                                                       simd_cols_for(xsize, simd_lanes),
                                                                       reinterpret_cast<unsigned long long*>(nan_count),
-                                                                      sink);
+                                                                      sink, clear_other);
     VS_CHECK_LAUNCH(ctx, "k_grid_finalize<u32, peer>");
     return VS_OK;
 }
@@ -361,7 +177,7 @@ int vs_grid_finalize_occ(vs_ctx* ctx, const uint32_t* keygrid, int xsize, int ys
     k_grid_finalize<uint32_t, OccSink><<<grid, kThreads, 0, stream>>>(keygrid, xsize, ysize, nullptr, dsm_out,
                                                                      simd_cols_for(xsize, simd_lanes),
                                                                      reinterpret_cast<unsigned long long*>(nan_count),
-                                                                     sink);
+                                                                     sink, nullptr);
     VS_CHECK_LAUNCH(ctx, "k_grid_finalize<u32, occ>");
     return VS_OK;
 }
@@ -369,10 +185,9 @@ int vs_grid_finalize_occ(vs_ctx* ctx, const uint32_t* keygrid, int xsize, int ys
 int vs_finalize_tma_try(vs_ctx* ctx, bool keys, const void* in, int in_rows, int in_row0, int W, int H, int row_begin,
                         int row_end, float* out, int simd_cols, unsigned long long* nan_count, cudaStream_t stream);
 
-extern "C" {
-
-int vs_grid_finalize(vs_ctx* ctx, const uint32_t* keygrid, int32_t xsize, int32_t ysize, float* dsm_out, int simd_lanes,
-                     uint64_t* nan_count, void* stream_) {
+// Stage B of one view; clear_other: see k_grid_finalize (nullptr: nothing to zero).
+int vs_grid_finalize_impl(vs_ctx* ctx, const uint32_t* keygrid, int32_t xsize, int32_t ysize, float* dsm_out, int simd_lanes,
+                          uint64_t* nan_count, void* stream_, uint32_t* clear_other) {
     VS_REQUIRE(ctx != nullptr, "vs_grid_finalize: NULL context");
     VS_REQUIRE(xsize > 0 && ysize > 0, "vs_grid_finalize: grid size must be positive");
     VS_REQUIRE(keygrid != nullptr && dsm_out != nullptr, "vs_grid_finalize: NULL array");
@@ -381,23 +196,30 @@ int vs_grid_finalize(vs_ctx* ctx, const uint32_t* keygrid, int32_t xsize, int32_
     if (!guard.ok) return vs_cuda_fail(cudaGetLastError(), "cudaSetDevice");
     cudaStream_t stream = (cudaStream_t)stream_;
     if (nan_count) VS_CUDA(cudaMemsetAsync(nan_count, 0, sizeof(uint64_t), stream));
-    if (!ctx->no_tma) {   // Blackwell path: persistent CTAs fed by TMA (finalize_tma.cu)
+    if (!ctx->no_tma && clear_other == nullptr) {   // opt-in: persistent CTAs fed by TMA (finalize_tma.cu)
         const int r = vs_finalize_tma_try(ctx, true, keygrid, ysize, 0, xsize, ysize, 0, ysize, dsm_out,
                                           simd_cols_for(xsize, simd_lanes),
                                           reinterpret_cast<unsigned long long*>(nan_count), stream);
         if (r < 0) return VS_ERR_CUDA;
         if (r > 0) return VS_OK;
     }
-    if (ctx->k2_mode == 2)                                                  // dense: the float-space kernel below is the default
+    if (ctx->k2_mode == 2 && clear_other == nullptr)                        // dense: the float-space kernel below is the default
         return vs_launch_finalize_keys(ctx, keygrid, xsize, ysize, dsm_out, simd_cols_for(xsize, simd_lanes),
                                        reinterpret_cast<unsigned long long*>(nan_count), stream);
     dim3 grid((xsize + TW - 1) / TW, (ysize + TH - 1) / TH);
     k_grid_finalize<uint32_t, NoSink><<<grid, kThreads, 0, stream>>>(keygrid, xsize, ysize, nullptr, dsm_out,
                                                                     simd_cols_for(xsize, simd_lanes),
                                                                     reinterpret_cast<unsigned long long*>(nan_count),
-                                                                    NoSink());
+                                                                    NoSink(), clear_other);
     VS_CHECK_LAUNCH(ctx, "k_grid_finalize<u32>");
     return VS_OK;
+}
+
+extern "C" {
+
+int vs_grid_finalize(vs_ctx* ctx, const uint32_t* keygrid, int32_t xsize, int32_t ysize, float* dsm_out, int simd_lanes,
+                     uint64_t* nan_count, void* stream_) {
+    return vs_grid_finalize_impl(ctx, keygrid, xsize, ysize, dsm_out, simd_lanes, nan_count, stream_, nullptr);
 }
 
 int vs_grid_finalize64(vs_ctx* ctx, const uint64_t* keygrid64, int32_t xsize, int32_t ysize, double* filled64,
@@ -412,7 +234,7 @@ int vs_grid_finalize64(vs_ctx* ctx, const uint64_t* keygrid64, int32_t xsize, in
     dim3 grid((xsize + TW - 1) / TW, (ysize + TH - 1) / TH);
     k_grid_finalize<unsigned long long, NoSink><<<grid, kThreads, 0, stream>>>(
         reinterpret_cast<const unsigned long long*>(keygrid64), xsize, ysize, filled64, blurred32,
-        simd_cols_for(xsize, simd_lanes), nullptr, NoSink());
+        simd_cols_for(xsize, simd_lanes), nullptr, NoSink(), nullptr);
     VS_CHECK_LAUNCH(ctx, "k_grid_finalize<u64>");
     return VS_OK;
 }

@@ -3,10 +3,65 @@
 
 bool vs_peer_plan_for(const vs_ctx* ctx, const float* plane, int64_t plane_stride, VsPeerPlan* plan);
 int vs_grid_finalize_peer(vs_ctx* ctx, const uint32_t* keygrid, int xsize, int ysize, float* dsm_out, int simd_lanes,
-                          uint64_t* nan_count, const VsPeerPlan& plan, cudaStream_t stream);
+                          uint64_t* nan_count, const VsPeerPlan& plan, cudaStream_t stream, uint32_t* clear_other);
+int vs_grid_finalize_impl(vs_ctx* ctx, const uint32_t* keygrid, int32_t xsize, int32_t ysize, float* dsm_out, int simd_lanes,
+                          uint64_t* nan_count, void* stream_, uint32_t* clear_other);
 int vs_grid_finalize_occ(vs_ctx* ctx, const uint32_t* keygrid, int xsize, int ysize, float* dsm_out, int simd_lanes,
                          uint64_t* nan_count, const VsOccPlan& plan, cudaStream_t stream);
 int vs_launch_clear_touched(vs_ctx* ctx, uint32_t* keygrid, unsigned char* touched, int xsize, int ysize, cudaStream_t stream);
+bool vs_stage_ab_eligible(const vs_ctx* ctx, bool want_stats, bool sparse);
+int vs_stage_ab_run(vs_ctx* ctx, int n_views, const float* const* depth, const int32_t* H, const int32_t* W,
+                    const double* inv_proj_mats, float* dsm_stack, int64_t plane_stride, int simd_lanes,
+                    uint64_t* nan_counts, int ns, cudaStream_t* streams);
+
+// Co-scheduled path (stage_ab.cu): one kernel per view step does stage B of the previous view and stage A of the next.
+static int views_to_dsm_ab(vs_ctx* ctx, int n_views, const float* const* depth, const int32_t* H, const int32_t* W,
+                           const double* inv_proj_mats, float* dsm_stack, int64_t plane_stride, int simd_lanes,
+                           uint64_t* nan_counts, cudaStream_t stream) {
+    const size_t cells = (size_t)ctx->aoi.xsize * ctx->aoi.ysize;
+    int ns = ctx->ab_streams < ctx->n_streams ? ctx->ab_streams : ctx->n_streams;
+    if (ns > n_views) ns = n_views;
+    int rc = vs_ensure_side_streams(ctx, ns);
+    if (rc) return rc;
+    if (ctx->keygrid_ab_cells < cells) {
+        for (int i = 0; i < VS_MAX_STREAMS; ++i)
+            for (int k = 0; k < 3; ++k) {
+                if (ctx->d_keygrid_ab[i][k]) cudaFree(ctx->d_keygrid_ab[i][k]);
+                ctx->d_keygrid_ab[i][k] = nullptr;
+            }
+        ctx->keygrid_ab_cells = 0;
+    }
+    for (int i = 0; i < ns; ++i)
+        for (int k = 0; k < 3; ++k)
+            if (!ctx->d_keygrid_ab[i][k]) VS_CUDA(cudaMalloc(&ctx->d_keygrid_ab[i][k], cells * sizeof(uint32_t)));
+    ctx->keygrid_ab_cells = cells;
+    const size_t need = 2 * (size_t)(n_views + ns);
+    if (ctx->ab_counters_ints < need) {
+        if (ctx->d_ab_counters) cudaFree(ctx->d_ab_counters);
+        ctx->d_ab_counters = nullptr;
+        ctx->ab_counters_ints = 0;
+        VS_CUDA(cudaMalloc(&ctx->d_ab_counters, need * sizeof(int)));
+        ctx->ab_counters_ints = need;
+    }
+    VS_CUDA(cudaMemsetAsync(ctx->d_ab_counters, 0, need * sizeof(int), stream));
+    VS_CUDA(cudaEventRecord(ctx->fork_event, stream));
+    cudaStream_t lanes[VS_MAX_STREAMS];
+    for (int i = 0; i < ns; ++i) {
+        lanes[i] = ctx->side_stream[i];
+        VS_CUDA(cudaStreamWaitEvent(lanes[i], ctx->fork_event, 0));
+    }
+    rc = vs_stage_ab_run(ctx, n_views, depth, H, W, inv_proj_mats, dsm_stack, plane_stride, simd_lanes, nan_counts, ns, lanes);
+    // join even after an error: the caller's stream stays ordered after everything enqueued here
+    const std::string first_error = rc ? std::string(vs_last_error()) : std::string();
+    for (int i = 0; i < ns; ++i) {
+        if (cudaEventRecord(ctx->join_event[i], lanes[i]) != cudaSuccess ||
+            cudaStreamWaitEvent(stream, ctx->join_event[i], 0) != cudaSuccess) {
+            if (rc == VS_OK) rc = vs_cuda_fail(cudaGetLastError(), "vs_views_to_dsm: join");
+        }
+    }
+    if (!first_error.empty()) vs_set_error(first_error);
+    return rc;
+}
 
 extern "C" {
 
@@ -26,6 +81,13 @@ int vs_views_to_dsm(vs_ctx* ctx, int32_t n_views, const float* const* depth, con
     cudaStream_t stream = (cudaStream_t)stream_;
     VsDeviceGuard guard(ctx->device);
     if (!guard.ok) return vs_cuda_fail(cudaGetLastError(), "cudaSetDevice");
+    {
+        const bool sparse_mode = ctx->k2_mode != 1 && ctx->poly.degree > 0 &&
+                                 (ctx->xch_on ? ctx->xch.occ_words > 0 : ctx->occ != nullptr);
+        if (vs_stage_ab_eligible(ctx, stats != nullptr, sparse_mode))
+            return views_to_dsm_ab(ctx, n_views, depth, H, W, inv_proj_mats, dsm_stack, plane_stride, simd_lanes, nan_counts,
+                                   stream);
+    }
     if (ctx->timing) {
         const size_t need = ctx->ev_used + 3 * (size_t)n_views;
         while (ctx->ev_pool.size() < need) {
@@ -83,6 +145,29 @@ int vs_views_to_dsm(vs_ctx* ctx, int32_t n_views, const float* const* depth, con
             VS_CUDA(cudaMemsetAsync(ctx->d_touched[i], 0, n_tiles, st));
         }
     }
+    // Dense mode: every internal stream alternates between TWO key grids.  Stage B of a view zeroes, tile by tile, the grid
+    // the previous view of its stream used (k_grid_finalize: clear_other), which the next view's stage A then scatters
+    // into -- instead of a whole-grid memset in front of every stage A (50 x 16.8 MB memset nodes per C2 step).  Both
+    // grids of a stream are zeroed once per call.  (Key-space / TMA variants of stage B keep the memset per view.)
+    const bool fold_clear = !sparse && ctx->k2_mode != 2 && ctx->no_tma && ctx->fold_clear;
+    if (fold_clear) {
+        const int n_used = dual ? NS : 1;
+        if (ctx->keygrid_alt_cells < (size_t)xs * ys) {
+            for (int i = 0; i < VS_MAX_STREAMS; ++i) {
+                if (ctx->d_keygrid_alt[i]) cudaFree(ctx->d_keygrid_alt[i]);
+                ctx->d_keygrid_alt[i] = nullptr;
+            }
+            ctx->keygrid_alt_cells = 0;
+        }
+        for (int i = 0; i < n_used; ++i)
+            if (!ctx->d_keygrid_alt[i]) VS_CUDA(cudaMalloc(&ctx->d_keygrid_alt[i], (size_t)xs * ys * sizeof(uint32_t)));
+        ctx->keygrid_alt_cells = (size_t)xs * ys;
+        for (int i = 0; i < n_used; ++i) {
+            cudaStream_t st = dual ? ctx->side_stream[i] : stream;
+            VS_CUDA(cudaMemsetAsync(i ? ctx->d_keygrid_extra[i] : keygrid, 0, (size_t)xs * ys * sizeof(uint32_t), st));
+            VS_CUDA(cudaMemsetAsync(ctx->d_keygrid_alt[i], 0, (size_t)xs * ys * sizeof(uint32_t), st));
+        }
+    }
     // On a per-view error the loop stops, but the side streams are still joined into the caller's stream below: the
     // work already enqueued stays ordered before whatever the caller enqueues next (and a stream capture in progress
     // stays joinable).  Planes [0, v) of dsm_stack are then complete, plane v onwards is undefined.
@@ -91,8 +176,18 @@ int vs_views_to_dsm(vs_ctx* ctx, int32_t n_views, const float* const* depth, con
         const int si = dual ? v % NS : 0;
         cudaStream_t st = dual ? ctx->side_stream[si] : stream;
         uint32_t* kg = si ? ctx->d_keygrid_extra[si] : keygrid;
+        uint32_t* kg_other = nullptr;
+        if (fold_clear) {
+            const int turn = dual ? v / NS : v;       // how many views this stream has taken before
+            kg_other = ctx->d_keygrid_alt[si];
+            if (turn & 1) {
+                uint32_t* t = kg;
+                kg = kg_other;
+                kg_other = t;
+            }
+        }
         ctx->cur_touched = sparse ? ctx->d_touched[si] : nullptr;
-        if (!sparse) {
+        if (!sparse && !fold_clear) {
             rc = vs_keygrid_clear(ctx, kg, (int64_t)xs * ys, 4, st);
             if (rc) break;
         }
@@ -109,7 +204,8 @@ int vs_views_to_dsm(vs_ctx* ctx, int32_t n_views, const float* const* depth, con
                 rc = VS_ERR_INVALID;
                 break;
             }
-            rc = vs_grid_finalize_peer(ctx, kg, xs, ys, plane, simd_lanes, nan_counts ? nan_counts + v : nullptr, plan, st);
+            rc = vs_grid_finalize_peer(ctx, kg, xs, ys, plane, simd_lanes, nan_counts ? nan_counts + v : nullptr, plan, st,
+                                       plan.occ_words > 0 ? nullptr : kg_other);
         } else if (ctx->occ != nullptr) {   // record which tiles of this plane hold data (vs_set_occupancy)
             const ptrdiff_t d = plane - ctx->occ_stack_base;
             const int64_t g = ctx->occ_view0 + (plane_stride > 0 ? d / plane_stride : 0);
@@ -125,7 +221,7 @@ int vs_views_to_dsm(vs_ctx* ctx, int32_t n_views, const float* const* depth, con
             op.view = (int)g;
             rc = vs_grid_finalize_occ(ctx, kg, xs, ys, plane, simd_lanes, nan_counts ? nan_counts + v : nullptr, op, st);
         } else {
-            rc = vs_grid_finalize(ctx, kg, xs, ys, plane, simd_lanes, nan_counts ? nan_counts + v : nullptr, st);
+            rc = vs_grid_finalize_impl(ctx, kg, xs, ys, plane, simd_lanes, nan_counts ? nan_counts + v : nullptr, st, kg_other);
         }
         if (rc) break;
         if (sparse) {   // leave the key grid of this stream empty again: clear the touched tiles, reset their marks
@@ -155,6 +251,12 @@ int vs_set_streams(vs_ctx* ctx, int n_streams) {
     VS_REQUIRE(ctx != nullptr, "vs_set_streams: NULL context");
     VS_REQUIRE(n_streams >= 1 && n_streams <= VS_MAX_STREAMS, "vs_set_streams: n_streams must be 1..4");
     ctx->n_streams = n_streams;
+    return VS_OK;
+}
+
+int vs_set_coschedule(vs_ctx* ctx, int enable) {
+    VS_REQUIRE(ctx != nullptr, "vs_set_coschedule: NULL context");
+    ctx->ab_on = enable != 0;
     return VS_OK;
 }
 

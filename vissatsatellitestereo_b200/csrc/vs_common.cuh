@@ -84,6 +84,9 @@ struct vs_ctx {
     cudaEvent_t fork_event, join_event[VS_MAX_STREAMS];
     uint32_t* d_keygrid_extra[VS_MAX_STREAMS];   // [0] unused: stream 0 scatters into the caller's key grid
     size_t keygrid_extra_cells;
+    uint32_t* d_keygrid_alt[VS_MAX_STREAMS];     // second key grid of every internal stream (stage B zeroes the other one)
+    size_t keygrid_alt_cells;
+    bool fold_clear;    // VISSAT_FOLD_CLEAR=0: keep the whole-grid memset per view (A/B)
     int n_streams;      // VISSAT_STREAMS=1..4 (default 4: measured 4.66 / 3.78 / 3.49 / 3.45 ms per C2 step for 1..4)
     // optional per-view kernel timing of vs_views_to_dsm
     // peer-store exchange of stage B (exchange.cu)
@@ -102,6 +105,13 @@ struct vs_ctx {
     // scratch of vs_fuse_views_sparse: per-bin tile lists (fuse.cu)
     int* d_fuse_plan;
     size_t fuse_plan_ints;
+    // co-scheduled stage A+B path (stage_ab.cu): three rotating key grids per internal stream, two queue counters per launch
+    uint32_t* d_keygrid_ab[VS_MAX_STREAMS][3];
+    size_t keygrid_ab_cells;
+    int* d_ab_counters;
+    size_t ab_counters_ints;
+    bool ab_on;         // vs_set_coschedule / VISSAT_AB (default on)
+    int ab_streams;     // VISSAT_AB_STREAMS (default 2): internal streams of the co-scheduled path
     bool timing;
     std::vector<cudaEvent_t> ev_pool;   // 3 events per logged view: before A, between A and B, after B
     size_t ev_used;

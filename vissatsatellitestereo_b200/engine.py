@@ -187,6 +187,10 @@ class DsmEngine:
     def set_streams(self, n):
         check(lib.vs_set_streams(self.ctx.handle, int(n)), 'vs_set_streams')
 
+    def set_coschedule(self, enable):
+        """Co-scheduled stage A+B kernel of views_to_dsm on (default) / off (the separate stage-A and stage-B kernels)."""
+        check(lib.vs_set_coschedule(self.ctx.handle, 1 if enable else 0), 'vs_set_coschedule')
+
     def set_timing(self, enable):
         check(lib.vs_set_timing(self.ctx.handle, 1 if enable else 0), 'vs_set_timing')
 
