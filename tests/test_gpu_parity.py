@@ -149,6 +149,17 @@ def test_fusion_bit_exact_vs_numpy(eng_mod, lanes, V):
     cube[:, 0, 2] = 7.25
     cube[:, 1, :] = np.round(cube[:, 1, :])          # many ties
     cube[:, 2, :] = np.where(rng.random((V, W)) < 0.5, 3.0, 4.0).astype(np.float32)
+    # inputs that are NOT alike across the lanes of the multi-lane kernels (lane = view mod 4 / 8 / 32): views alternating
+    # between two levels, levels by view mod 8, a ramp over the view index, one lane far away -- the split search of
+    # k_fuse_large must take its bounded number of exchanges and finish with the bisection
+    vi = np.arange(V, dtype=np.float32)[:, None]
+    noise = rng.normal(size=(V, W)).astype(np.float32)
+    cube[:, 3, :] = np.where(vi % 2 == 0, 10.0, 50.0) + noise
+    cube[:, 4, :] = 5.0 * (vi % 8) + 0.1 * noise
+    cube[:, 5, :] = 0.37 * vi + 0.01 * noise
+    cube[:, 6, :] = np.where(vi % 8 == 3, -500.0, 20.0) + noise
+    cube[:, 7, :] = np.where(vi % 32 < 16, 1.0, 2.0) + 0.001 * noise
+    cube[rng.random(cube.shape) < 0.02] = np.nan
     want = op.fuse_dsms([cube[v].copy() for v in range(V)], blur=False)
     got = eng.fuse(torch.from_numpy(cube).cuda()).cpu().numpy()
     assert _eq(got, want)

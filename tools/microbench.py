@@ -77,7 +77,9 @@ def main():
         base = torch.stack([eng.view_dsm(depths[v], mats[v]).clone() for v in range(4)])
         for V, rows in ((8, 2048), (16, 2048), (24, 2048), (32, 2048), (40, 2048), (50, 2048), (64, 2048), (100, 1024),
                         (200, 512), (400, 256)):
-            idx = torch.arange(V, device=dev) % 4
+            # VISSAT_MB_SHUFFLE=1: base view drawn at random per view (lanes of the multi-lane kernels see alike runs);
+            # default: view v uses base view v % 4 (lane = view mod 4 / 8: every lane sees ONE base view)
+            idx = torch.randint(0, 4, (V,), device=dev) if os.environ.get('VISSAT_MB_SHUFFLE') == '1' else torch.arange(V, device=dev) % 4
             stack = (base[idx, :rows] + torch.randn((V, 1, 1), device=dev) * 0.5).contiguous()
             stack[torch.rand(stack.shape, device=dev) < 0.1] = float('nan')
             out = torch.empty((rows, eng.e_size), dtype=torch.float32, device=dev)

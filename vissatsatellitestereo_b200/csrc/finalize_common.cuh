@@ -77,6 +77,7 @@ __device__ __forceinline__ float median9_exact(const float* r0, const float* r1,
 // Besides the caller's array, stage B can store every output row into the row-band stacks of the ranks that fuse it
 // (multi-GPU exchange through peer-mapped memory).  NoSink compiles to nothing.
 struct NoSink {
+    __device__ __forceinline__ void prepare(int, int, int) const {}         // every thread, once per tile, before a barrier
     __device__ __forceinline__ void store4(int, int, int, const float4&) const {}
     __device__ __forceinline__ void store1(int, int, int, float) const {}
     __device__ __forceinline__ void mark_tile(int, int, int) const {}       // one thread per CTA calls it
@@ -86,6 +87,7 @@ struct NoSink {
 // Records which (tile, view) pairs hold data (vs_set_occupancy); no peer stores.
 struct OccSink {
     VsOccPlan o;
+    __device__ __forceinline__ void prepare(int, int, int) const {}
     __device__ __forceinline__ void store4(int, int, int, const float4&) const {}
     __device__ __forceinline__ void store1(int, int, int, float) const {}
     __device__ __forceinline__ void mark_tile(int tx, int ty, int) const {
@@ -130,15 +132,42 @@ struct PeerSink {
         if (j > 0 && y - p.row0[j] < p.halo && p.row0[j] > p.row0[j - 1]) f(j - 1);
         if (j + 1 < p.n && p.row0[j + 1] - y <= p.halo && p.row0[j + 2] > p.row0[j + 1]) f(j + 1);
     }
+    // The 16-byte stores of a tile go through a per-tile table in shared memory: for each of its 32 rows the row starts
+    // in the (up to three) band stacks that receive it, worked out once per tile by 32 threads (prepare) instead of by
+    // every thread for every segment (band search + halo tests: ~40 instructions per store, +20 % on the kernel).
+    static __device__ __forceinline__ float** row_table() {
+        __shared__ float* t[TH * 3];
+        return t;
+    }
+    static __device__ __forceinline__ int* row_info() {   // [r] = destinations of tile row r, [TH] = first grid row of the tile
+        __shared__ int t[TH + 1];
+        return t;
+    }
+    __device__ __forceinline__ void prepare(int ty0, int H, int W) const {
+        const int r = threadIdx.x;
+        if (r < TH) {
+            int n = 0;
+            const int y = ty0 + r;
+            if (y < H) each_dest(y, [&](int j) { row_table()[3 * r + n++] = at(j, y, 0, W); });
+            row_info()[r] = n;
+        }
+        if (r == 0) row_info()[TH] = ty0;
+    }
     __device__ __forceinline__ void store4(int y, int x, int W, const float4& v) const {
-        each_dest(y, [&](int j) {
-            float* d = at(j, y, x, W);
-            if ((reinterpret_cast<uintptr_t>(d) & 15) == 0) {
-                *reinterpret_cast<float4*>(d) = v;
-            } else {   // odd row pitch
-                d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        const int r = y - row_info()[TH];
+        const int nd = row_info()[r];
+        float* const* t = row_table() + 3 * r;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            if (k < nd) {
+                float* d = t[k] + x;
+                if ((reinterpret_cast<uintptr_t>(d) & 15) == 0) {
+                    *reinterpret_cast<float4*>(d) = v;
+                } else {   // odd row pitch
+                    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+                }
             }
-        });
+        }
     }
     __device__ __forceinline__ void store1(int y, int x, int W, float v) const {
         each_dest(y, [&](int j) { *at(j, y, x, W) = v; });

@@ -237,6 +237,7 @@ k_grid_finalize_keys(const uint32_t* __restrict__ keygrid, int W, int H, float* 
     const int tid = threadIdx.x;
     const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH;
     if (tid == 0) s_has_nan = 0;
+    sink.prepare(ty0, H, W);                                 // PeerSink: per-row destination table of this tile
     __syncthreads();
     if (touched != nullptr) {   // sparse mode: a tile whose 3x3 tile neighbourhood got no key is empty without looking
         int any = 0;

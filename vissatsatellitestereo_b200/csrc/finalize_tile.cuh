@@ -45,6 +45,7 @@ __device__ __forceinline__ void grid_finalize_tile(const int bx, const int by, c
     const int tid = threadIdx.x;
     const int tx0 = bx * TW, ty0 = by * TH;
     if (tid == 0) s_has_nan = 0;
+    sink.prepare(ty0, H, W);                                 // PeerSink: per-row destination table of this tile
     __syncthreads();
 
     // 1. decode keys (+2 halo).  Key 0 (= empty, also used outside the grid) decodes to NaN, and the fill only

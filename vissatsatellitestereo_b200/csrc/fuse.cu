@@ -327,6 +327,59 @@ __device__ __forceinline__ void group_select(const uint32_t* __restrict__ run, i
     }
 }
 
+template <int LANES>
+__device__ __forceinline__ uint32_t group_min(uint32_t v, unsigned mask) {
+#pragma unroll
+    for (int o = LANES / 2; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(mask, v, o));
+    return v;
+}
+
+// The same two order statistics by a SPLIT search instead of a bit-wise bisection (round 2).  Lane l keeps p_l = how many
+// of its sorted keys belong to the r_hi smallest of the union (sum of p_l = r_hi).  The split is right when the largest
+// key left of the splits, A, is <= the smallest key right of them, B; then B has rank r_hi and A rank r_hi - 1.  The runs
+// of a cell are interleaved views (lane = view mod LANES), i.e. statistically alike, so the balanced start p_l ~ r_hi /
+// LANES is a few exchanges away from the answer (2 probes per iteration against 32 bisection steps of 3 probes);
+// every iteration moves keys from lanes that hold too many of the small ones to lanes that hold too few.  An input that
+// needs more than kSplitIters exchanges (views that alternate systematically between two levels) finishes with the
+// bisection above, restricted to the bracket [B, A] the exchanges have reached, so the worst case stays bounded.  Keys: 0 is below every key, the run pads 0xffffffff above.
+constexpr int kSplitIters = 16;
+template <int LANES, int NVL>
+__device__ __forceinline__ void group_select_split(const uint32_t* __restrict__ run, int r_hi, bool want_lo, unsigned mask,
+                                                   uint32_t& k_hi_out, uint32_t& k_lo_out) {
+    const int me = threadIdx.x & 31;
+    const int lane = me & (LANES - 1);
+    int p = r_hi / LANES + (lane < (r_hi & (LANES - 1)) ? 1 : 0);
+    uint32_t A = 0xffffffffu, B = 0u;
+    for (int it = 0; it < kSplitIters; ++it) {
+        const uint32_t a = p > 0 ? run[(p - 1) * LANES] : 0u;
+        const uint32_t b = run[p * LANES];                   // p <= NVL < RunPad: a pad at worst
+        A = group_max<LANES>(a, mask);
+        B = group_min<LANES>(b, mask);
+        if (A <= B) {                                        // group-uniform
+            k_hi_out = B;
+            k_lo_out = want_lo ? A : B;
+            return;
+        }
+        // A > B.  Every lane whose top-left key exceeds B would gain from handing it over, every lane whose first right
+        // key is below A from taking one: m = min(#over, #under) lanes of each kind move their split by one, so that
+        // the sum of the p_l stays r_hi (if exactly one pair is out of order this is the single exchange A <-> B).
+        // Any sequence of such moves is safe -- only the exit test above decides -- and all lanes adjust in parallel:
+        // the iteration count is the largest per-lane offset from the balanced start, not the sum.
+        const unsigned over = __ballot_sync(mask, a > B), under = __ballot_sync(mask, b < A);
+        const int m = min(__popc(over), __popc(under));
+        const unsigned below_me = (1u << me) - 1u;
+        const bool dec = a > B && __popc(over & below_me) < m;
+        const bool inc = b < A && __popc(under & below_me) < m;
+        p += (inc ? 1 : 0) - (dec ? 1 : 0);
+    }
+    // Not there yet.  With r_hi keys left of the splits, A among them and B < A right of them: fewer than r_hi keys are
+    // below B and more than r_hi are <= A, so B <= answer <= A, and the bisection only has to resolve the bits below the
+    // common prefix of the two.
+    const int hb = 31 - __clz(A ^ B);                        // highest differing bit (A != B here)
+    const uint32_t prefix = A & ~((2u << hb) - 1u);
+    group_select<LANES, NVL>(run, r_hi, want_lo, mask, prefix, hb, k_hi_out, k_lo_out);
+}
+
 // nanmean of the survivors of one cell in numpy's pairwise order, computed by the LANES threads of the cell's group
 // (lane j < 8 owns numpy's accumulator r[j]); the views are re-read from L2.  Every lane returns the mean.
 // `present(v)`: whether view v takes part at all (dense stacks: always; sparse fusion: the tile's occupancy bit -- an
@@ -491,7 +544,7 @@ k_fuse_large(const float* __restrict__ views, int64_t plane_stride, int V, int64
     // 3. median
     const int ilo = (k - 1) >> 1, ihi = k >> 1;
     uint32_t khi, klo;
-    group_select<LANES, NVL>(run, ihi, ilo != ihi, gmask, 0u, 31, khi, klo);
+    group_select_split<LANES, NVL>(run, ihi, ilo != ihi, gmask, khi, klo);
     const float med = __fdiv_rn(__fadd_rn(vs_unkey32(klo), vs_unkey32(khi)), 2.0f);
     __syncwarp(gmask);
 
@@ -502,7 +555,7 @@ k_fuse_large(const float* __restrict__ views, int64_t plane_stride, int V, int64
 #pragma unroll
     for (int i = 0; i < NVL; ++i) run[i * LANES] = vs_key32(s[i]);
     __syncwarp(gmask);
-    group_select<LANES, NVL>(run, ihi, ilo != ihi, gmask, 0x80000000u, 30, khi, klo);   // deviations are >= 0
+    group_select_split<LANES, NVL>(run, ihi, ilo != ihi, gmask, khi, klo);   // deviations are >= 0
     const float mad = __fdiv_rn(__fadd_rn(vs_unkey32(klo), vs_unkey32(khi)), 2.0f);
 
     // 5. nanmean of the survivors in numpy's pairwise order
@@ -880,7 +933,7 @@ k_fuse_sparse_large(const __grid_constant__ SparseGeom g, int bin, int VS, int s
             __syncwarp(gmask);
             const int ilo = (k - 1) >> 1, ihi = k >> 1;
             uint32_t khi, klo;
-            group_select<LANES, NVL>(run, ihi, ilo != ihi, gmask, 0u, 31, khi, klo);
+            group_select_split<LANES, NVL>(run, ihi, ilo != ihi, gmask, khi, klo);
             const float med = __fdiv_rn(__fadd_rn(vs_unkey32(klo), vs_unkey32(khi)), 2.0f);
             __syncwarp(gmask);
 #pragma unroll
@@ -889,7 +942,7 @@ k_fuse_sparse_large(const __grid_constant__ SparseGeom g, int bin, int VS, int s
 #pragma unroll
             for (int i = 0; i < NVL; ++i) run[i * LANES] = vs_key32(s[i]);
             __syncwarp(gmask);
-            group_select<LANES, NVL>(run, ihi, ilo != ihi, gmask, 0x80000000u, 30, khi, klo);
+            group_select_split<LANES, NVL>(run, ihi, ilo != ihi, gmask, khi, klo);
             const float mad = __fdiv_rn(__fadd_rn(vs_unkey32(klo), vs_unkey32(khi)), 2.0f);
             const float mean = sum_survivors<LANES>(g.views, cell, g.plane_stride, g.V, med, mad, lane, gmask, present);
             if (lane == 0) g.out[cell] = mean;
