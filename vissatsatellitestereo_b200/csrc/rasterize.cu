@@ -148,7 +148,7 @@ k_unproject_scatter(RasterParams p_in, PolyCoefs pc, const VsExactParams* __rest
                 if (o == 2) {
                     key[i] = vs_key32((float)val[i]);
                 } else {
-                    const int q = __double2int_rd(val[i]);  // floor, lib/proj_to_grid.py:42-43
+                    const int q = LEAN ? floor_to_int_fast(val[i]) : __double2int_rd(val[i]);  // floor, lib/proj_to_grid.py:42-43
                     if (o == 0) ci[i] = q; else ri[i] = q;
                     if (audit) {
                         const bool a = fabs(val[i] - rint(val[i])) < p.eps;

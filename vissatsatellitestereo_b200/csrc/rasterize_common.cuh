@@ -115,6 +115,18 @@ __device__ __forceinline__ double fast_rcp(double a) {
     return fma(r, e, r);
 }
 
+// floor(v) as an int for |v| < 2^31 without the XU pipe: adding 1.5 * 2^52 with round-toward-minus-infinity leaves
+// floor(v) in the low word of the sum (one FP64-pipe DADD.RM instead of an F2I.F64.FLOOR conversion; the conversions are
+// the most loaded pipe of stage A).  Exactly __double2int_rd(v) on that range; NaN / out-of-range inputs give garbage,
+// which the callers mask (such a point is never "in the box").  VISSAT_NO_MAGIC_FLOOR: A/B switch at compile time.
+__device__ __forceinline__ int floor_to_int_fast(double v) {
+#ifdef VISSAT_NO_MAGIC_FLOOR
+    return __double2int_rd(v);
+#else
+    return __double2loint(__dadd_rd(v, 6755399441055744.0));
+#endif
+}
+
 // One 4-pixel chunk that does not sit inside a single image row, or the ragged tail of the image: evaluated
 // pixel by pixel through the same device functions (rare: only when W is not a multiple of 4 / at the very end).
 template <int D, int D64>
@@ -237,7 +249,7 @@ __device__ __forceinline__ void scatter_chunk_lean(const RasterParams& p, const 
             if (o == 2) {
                 key[i] = vs_key32((float)val[i]);
             } else {
-                const int q = __double2int_rd(val[i]);  // floor, lib/proj_to_grid.py:42-43
+                const int q = floor_to_int_fast(val[i]);  // floor, lib/proj_to_grid.py:42-43
                 if (o == 0) ci[i] = q; else ri[i] = q;
             }
         }
