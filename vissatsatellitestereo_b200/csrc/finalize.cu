@@ -31,11 +31,11 @@ k_grid_finalize(const Key* __restrict__ keygrid, int W, int H, typename KeyTrait
     if (clear_other != nullptr) {
         const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH;
         if (sizeof(Key) == 4 && (W & 3) == 0 && (reinterpret_cast<uintptr_t>(clear_other) & 15) == 0 && tx0 + TW <= W) {
-            for (int i = threadIdx.x; i < TH * (TW / 4); i += kThreads) {
-                const int r = i / (TW / 4), c4 = i - r * (TW / 4);
-                if (ty0 + r < H)
-                    *reinterpret_cast<uint4*>(clear_other + (size_t)(ty0 + r) * W + tx0 + 4 * c4) = make_uint4(0u, 0u, 0u, 0u);
-            }
+            static_assert(TW == 64 && TH == 32 && kThreads == 256, "two 16-byte stores per thread: rows r and r + 16");
+            const int r = threadIdx.x >> 4, c4 = threadIdx.x & 15;
+            Key* q = clear_other + (size_t)(ty0 + r) * W + tx0 + 4 * c4;
+            if (ty0 + r < H) *reinterpret_cast<uint4*>(q) = make_uint4(0u, 0u, 0u, 0u);
+            if (ty0 + r + 16 < H) *reinterpret_cast<uint4*>(q + (size_t)16 * W) = make_uint4(0u, 0u, 0u, 0u);
         } else {
             for (int i = threadIdx.x; i < TH * TW; i += kThreads) {
                 const int r = i / TW, c = i - r * TW;
