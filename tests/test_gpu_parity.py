@@ -5,6 +5,7 @@ Bars (BASELINE.json north_star): cell indices, occupancy masks and median select
 cell edge or flip the strict `abs(x-med) > mad` test, the tests audit it instead of hiding it.
 """
 import json
+import os
 
 import cv2
 import numpy as np
@@ -491,3 +492,38 @@ def test_coscheduled_stage_ab_bit_identical_to_separate_kernels(eng_mod, lanes, 
     torch.cuda.synchronize()
     assert torch.equal(torch.nan_to_num(stack, nan=-1e9), torch.nan_to_num(want, nan=-1e9))
     eng.close()
+
+
+def test_fusion_split_search_variant_bit_exact(lanes):
+    """VISSAT_FUSE_SPLIT=1 (order statistics of the multi-lane fusion kernels by a split search with a bracketed bisection as
+    fallback; opt-in, read once per process -> a child process): bit-exact against numpy on random, tied and lane-structured
+    inputs, V = 257 (32 lanes) and 400 (8 lanes)."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, %r)
+from oracle import geodesy, pipeline as op
+from vissatsatellitestereo_b200 import engine as E, synthetic as S
+cfg = S.scaled(S.CONFIGS['C1'], views=1, depth=64, grid=32)
+eng = E.DsmEngine(S.make_aoi(cfg, geodesy), cfg.res, cfg.res, simd_lanes=%d)
+for V in (257, 400):
+    rng = np.random.default_rng(V)
+    H, W = 9, 41
+    cube = (30 + 5 * rng.normal(size=(V, H, W))).astype(np.float32)
+    cube[rng.random(cube.shape) < 0.3] = np.nan
+    vi = np.arange(V, dtype=np.float32)[:, None]
+    noise = rng.normal(size=(V, W)).astype(np.float32)
+    cube[:, 1, :] = np.round(cube[:, 1, :])
+    cube[:, 3, :] = np.where(vi %% 2 == 0, 10.0, 50.0) + noise
+    cube[:, 4, :] = 5.0 * (vi %% 8) + 0.1 * noise
+    cube[:, 5, :] = 0.37 * vi + 0.01 * noise
+    cube[:, 6, :] = np.where(vi %% 8 == 3, -500.0, 20.0) + noise
+    want = op.fuse_dsms([cube[v].copy() for v in range(V)], blur=False)
+    got = eng.fuse(torch.from_numpy(cube).cuda()).cpu().numpy()
+    assert np.array_equal(got, want, equal_nan=True), V
+print('SPLIT_OK')
+''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), lanes)
+    env = dict(os.environ, VISSAT_FUSE_SPLIT='1')
+    r = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and 'SPLIT_OK' in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

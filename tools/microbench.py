@@ -28,7 +28,8 @@ def timeit(fn, n=10, warm=3):
 def main():
     what = sys.argv[1:] or ['fuse', 'k1', 'k2', 'k4']
     cfg = S.SynthConfig(**S.CONFIGS['C2'].__dict__)
-    cfg.n_views = 4
+    NB = int(os.environ.get('VISSAT_MB_BASE', '4'))      # distinct synthetic views behind the fusion stacks
+    cfg.n_views = NB
     aoi = S.make_aoi(cfg, geo)
     eng = E.DsmEngine(aoi, cfg.res, cfg.res)
     eng.collect_stats = False
@@ -44,7 +45,7 @@ def main():
 
         def k1():
             eng.clear_keygrid()
-            eng.rasterize(depths[i[0] % 4], mats[i[0] % 4], clear=False)
+            eng.rasterize(depths[i[0] % NB], mats[i[0] % NB], clear=False)
             i[0] += 1
         t = timeit(k1, 20)
         print('k1 (clear + unproject_scatter) {:.1f} us/view  {:.1f} Gpix/s  {:.0f} GB/s'.format(t * 1e3, P / t / 1e6, 4 * P / t / 1e6))
@@ -74,12 +75,12 @@ def main():
         t = timeit(lambda: eng.median3x3(img, out=out), 20)
         print('k4 median3x3 {:.1f} us  {:.0f} GB/s (8 B/cell)'.format(t * 1e3, 8 * G / t / 1e6))
     if 'fuse' in what:
-        base = torch.stack([eng.view_dsm(depths[v], mats[v]).clone() for v in range(4)])
+        base = torch.stack([eng.view_dsm(depths[v], mats[v]).clone() for v in range(NB)])
         for V, rows in ((8, 2048), (16, 2048), (24, 2048), (32, 2048), (40, 2048), (50, 2048), (64, 2048), (100, 1024),
                         (200, 512), (400, 256)):
             # VISSAT_MB_SHUFFLE=1: base view drawn at random per view (lanes of the multi-lane kernels see alike runs);
             # default: view v uses base view v % 4 (lane = view mod 4 / 8: every lane sees ONE base view)
-            idx = torch.randint(0, 4, (V,), device=dev) if os.environ.get('VISSAT_MB_SHUFFLE') == '1' else torch.arange(V, device=dev) % 4
+            idx = torch.randint(0, NB, (V,), device=dev) if os.environ.get('VISSAT_MB_SHUFFLE') == '1' else torch.arange(V, device=dev) % NB
             stack = (base[idx, :rows] + torch.randn((V, 1, 1), device=dev) * 0.5).contiguous()
             stack[torch.rand(stack.shape, device=dev) < 0.1] = float('nan')
             out = torch.empty((rows, eng.e_size), dtype=torch.float32, device=dev)

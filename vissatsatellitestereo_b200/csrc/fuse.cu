@@ -334,7 +334,7 @@ __device__ __forceinline__ uint32_t group_min(uint32_t v, unsigned mask) {
     return v;
 }
 
-// The same two order statistics by a SPLIT search instead of a bit-wise bisection (round 2).  Lane l keeps p_l = how many
+// The same two order statistics by a SPLIT search instead of a bit-wise bisection (round 2; opt-in, see g_fuse_split).  Lane l keeps p_l = how many
 // of its sorted keys belong to the r_hi smallest of the union (sum of p_l = r_hi).  The split is right when the largest
 // key left of the splits, A, is <= the smallest key right of them, B; then B has rank r_hi and A rank r_hi - 1.  The runs
 // of a cell are interleaved views (lane = view mod LANES), i.e. statistically alike, so the balanced start p_l ~ r_hi /
@@ -343,9 +343,15 @@ __device__ __forceinline__ uint32_t group_min(uint32_t v, unsigned mask) {
 // needs more than kSplitIters exchanges (views that alternate systematically between two levels) finishes with the
 // bisection above, restricted to the bracket [B, A] the exchanges have reached, so the worst case stays bounded.  Keys: 0 is below every key, the run pads 0xffffffff above.
 constexpr int kSplitIters = 16;
+__device__ int g_fuse_split = 0;      // VISSAT_FUSE_SPLIT=1: try the split search first (measured: 1.34 vs 1.40 ms at V = 400 when
+                                      // the lanes' runs are alike, 1.69 ms when they are not -- so it is opt-in)
 template <int LANES, int NVL>
 __device__ __forceinline__ void group_select_split(const uint32_t* __restrict__ run, int r_hi, bool want_lo, unsigned mask,
                                                    uint32_t& k_hi_out, uint32_t& k_lo_out) {
+    if (!g_fuse_split) {              // uniform over the grid
+        group_select<LANES, NVL>(run, r_hi, want_lo, mask, 0u, 31, k_hi_out, k_lo_out);
+        return;
+    }
     const int me = threadIdx.x & 31;
     const int lane = me & (LANES - 1);
     int p = r_hi / LANES + (lane < (r_hi & (LANES - 1)) ? 1 : 0);
@@ -1165,6 +1171,15 @@ int launch_sparse_large(vs_ctx* ctx, const SparseGeom& g, int bin, cudaStream_t 
     return VS_OK;
 }
 
+static int fuse_select_mode_once() {
+    static const int rc = []() {
+        const char* e = getenv("VISSAT_FUSE_SPLIT");
+        const int v = (e && e[0] == '1') ? 1 : 0;
+        return v ? (int)cudaMemcpyToSymbol(g_fuse_split, &v, sizeof(int)) : 0;
+    }();
+    return rc;
+}
+
 template <int NV>
 int launch_small(vs_ctx* ctx, const float* views, int64_t plane_stride, int V, int64_t n_cells, float* out,
                  cudaStream_t stream) {
@@ -1190,6 +1205,7 @@ int launch_large_t(vs_ctx* ctx, const float* views, int64_t plane_stride, int V,
     int VS = LANES * RunPad<NVL>::value;
     VS += (9 - (VS & 31) + 32) & 31;  // row stride = 9 (mod 32): conflict-free tile stores, few conflicts on the runs
     const size_t smem = (size_t)CELLS * VS * sizeof(uint32_t);
+    fuse_select_mode_once();
     VS_CUDA(cudaFuncSetAttribute(k_fuse_large<LANES, NVL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t blocks = (n_cells + CELLS - 1) / CELLS;
     k_fuse_large<LANES, NVL><<<(unsigned)blocks, kLargeThreads, smem, stream>>>(views, plane_stride, V, n_cells, VS, out);
