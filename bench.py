@@ -542,6 +542,19 @@ def measure(cfg, total_views, block, world, rank, dev, steps, warmup, sparse, wa
                       ('' if world == 1 else ' per rank + NCCL row-band exchange + per-rank fused band to host')}
         if cfg.fuse and world == 1 and fused is not None:
             assert np.array_equal(host_fused.numpy(), fused.cpu().numpy(), equal_nan=True), 'e2e result differs'
+        # secondary: the same call when only the fused DSM is wanted on the host (no per-view DSMs back): the device->host
+        # direction is what the hosts of the GPU boxes are slowest at (tools/pcie_probe.py, profiles/r2b_pcie_probe_n8.txt)
+        if cfg.fuse and world == 1:
+            def e2e_fused_only():
+                eng.process_host(host_depths, mats, None, host_fused, stack=stack, fuse=True)
+            e2e_fused_only()
+            w0 = time.perf_counter()
+            for _ in range(n_e2e):
+                e2e_fused_only()
+            t_fo = (time.perf_counter() - w0) / n_e2e
+            res['e2e']['fused_only'] = {'value': mpix_step / t_fo, 'unit': UNIT, 'ms_per_step': 1e3 * t_fo,
+                                        'h2d_bytes_per_step': int(V * P * 4), 'd2h_bytes_per_step': int(G * 4),
+                                        'note': 'same API without views_out_host: per-view DSMs stay on the device'}
     if peer:
         xch.close()
     eng.close()
