@@ -453,7 +453,24 @@ __device__ __forceinline__ float sum_survivors(const float* __restrict__ views, 
                         bool keep = (t == t) && !(fabsf(__fsub_rn(t, y.med)) > y.mad);
                         r[m] = keep ? t : 0.0f;
                         cnt += keep;
-                        for (int i = 8; i < nfull; i += 8) {
+                        int i = 8;
+                        for (; i + 24 < nfull; i += 32) {        // four blocks of 8 per batch: the loads go out together
+                            float tt[4];
+                            bool pr[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                pr[j] = present(v0 + i + 8 * j);
+                                tt[j] = pr[j] ? __ldg(q + (j + 1) * step8) : CUDART_NAN_F;
+                            }
+                            q += 4 * step8;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {        // same order of additions as one by one
+                                keep = (tt[j] == tt[j]) && !(fabsf(__fsub_rn(tt[j], y.med)) > y.mad);
+                                if (pr[j]) r[m] = __fadd_rn(r[m], keep ? tt[j] : 0.0f);   // absent view: + 0, skipped
+                                cnt += keep;
+                            }
+                        }
+                        for (; i < nfull; i += 8) {
                             q += step8;
                             if (!present(v0 + i)) continue;       // + 0: no-op
                             t = __ldg(q);
@@ -503,13 +520,30 @@ k_fuse_large(const float* __restrict__ views, int64_t plane_stride, int V, int64
     const int tid = threadIdx.x;
     const int64_t cell0 = blockIdx.x * (int64_t)CELLS;
 
-    // 1. coalesced load: consecutive threads read consecutive cells of one view plane
-    for (int i = tid; i < CELLS * V; i += kLargeThreads) {
-        const int v = i / CELLS, c = i - v * CELLS;
-        const int64_t cell = cell0 + c;
-        float t = CUDART_NAN_F;
-        if (cell < n_cells) t = __ldg(views + (int64_t)v * plane_stride + cell);
-        s_tile[c * VS + v] = __float_as_uint(t);
+    // 1. coalesced load: consecutive threads read consecutive cells of one view plane.  Thread t owns cell t % CELLS and
+    //    views t / CELLS, + kLargeThreads / CELLS, ...; the loads of a batch of kLoadBatch views are all issued before
+    //    the first result is stored (the kernel has ~22 warps per SM to hide the latency of this phase with).
+    {
+        constexpr int VSTEP = kLargeThreads / CELLS;       // views between two loads of a thread
+        constexpr int kLoadBatch = 8;
+        const int c = tid % CELLS;
+        const bool cell_ok = cell0 + c < n_cells;
+        const float* __restrict__ src = views + cell0 + c;
+        uint32_t* __restrict__ dst = s_tile + c * VS;
+        for (int v0 = tid / CELLS; v0 < V; v0 += VSTEP * kLoadBatch) {
+            float t[kLoadBatch];
+#pragma unroll
+            for (int j = 0; j < kLoadBatch; ++j) {
+                const int v = v0 + j * VSTEP;
+                t[j] = CUDART_NAN_F;
+                if (cell_ok && v < V) t[j] = __ldg(src + (int64_t)v * plane_stride);
+            }
+#pragma unroll
+            for (int j = 0; j < kLoadBatch; ++j) {
+                const int v = v0 + j * VSTEP;
+                if (v < V) dst[v] = __float_as_uint(t[j]);
+            }
+        }
     }
     __syncthreads();
 
@@ -899,11 +933,27 @@ k_fuse_sparse_large(const __grid_constant__ SparseGeom g, int bin, int VS, int s
             const int64_t cell0 = (int64_t)(gy - g.row0) * g.W + gx0;
             const int n_cols = min(CELLS, g.W - gx0);
             __syncthreads();                                // previous pass done with s_tile
-            for (int i = tid; i < CELLS * n; i += kLargeThreads) {
-                const int slot = i / CELLS, c = i - slot * CELLS;
-                float t = CUDART_NAN_F;
-                if (c < n_cols) t = __ldg(g.views + (int64_t)s_list[slot] * g.plane_stride + cell0 + c);
-                s_tile[c * VS + slot] = __float_as_uint(t);
+            {   // loads of a batch of listed views in flight before the first store (see k_fuse_large)
+                constexpr int VSTEP = kLargeThreads / CELLS;
+                constexpr int kLoadBatch = 8;
+                const int c = tid % CELLS;
+                const bool cell_ok = c < n_cols;
+                const float* __restrict__ src = g.views + cell0 + c;
+                uint32_t* __restrict__ dst = s_tile + c * VS;
+                for (int s0 = tid / CELLS; s0 < n; s0 += VSTEP * kLoadBatch) {
+                    float t[kLoadBatch];
+#pragma unroll
+                    for (int j = 0; j < kLoadBatch; ++j) {
+                        const int slot = s0 + j * VSTEP;
+                        t[j] = CUDART_NAN_F;
+                        if (cell_ok && slot < n) t[j] = __ldg(src + (int64_t)s_list[slot] * g.plane_stride);
+                    }
+#pragma unroll
+                    for (int j = 0; j < kLoadBatch; ++j) {
+                        const int slot = s0 + j * VSTEP;
+                        if (slot < n) dst[slot] = __float_as_uint(t[j]);
+                    }
+                }
             }
             __syncthreads();
             const int c_local = tid / LANES, lane = tid % LANES;
