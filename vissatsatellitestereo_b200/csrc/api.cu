@@ -154,7 +154,16 @@ int vs_ctx_create(int device, vs_ctx** out) {
     }
     ctx->fork_event = nullptr;
     ctx->keygrid_extra_cells = 0;
-    for (int i = 0; i < VS_MAX_STREAMS; ++i) ctx->d_keygrid_alt[i] = nullptr;
+    for (int i = 0; i < VS_MAX_STREAMS; ++i) {
+        ctx->d_keygrid_alt[i] = nullptr;
+        ctx->prio_stream[i] = nullptr;
+        ctx->prio_ev_a[i] = ctx->prio_ev_b[i] = ctx->prio_join[i] = nullptr;
+    }
+    {
+        const char* pm = getenv("VISSAT_PRIO");
+        const int v = pm ? atoi(pm) : 0;
+        ctx->prio_mode = (v == 1 || v == 2) ? v : 0;
+    }
     ctx->keygrid_alt_cells = 0;
     {
         const char* fc = getenv("VISSAT_FOLD_CLEAR");
@@ -208,6 +217,10 @@ int vs_ctx_destroy(vs_ctx* ctx) {
         if (ctx->join_event[i]) cudaEventDestroy(ctx->join_event[i]);
         if (ctx->d_keygrid_extra[i]) cudaFree(ctx->d_keygrid_extra[i]);
         if (ctx->d_keygrid_alt[i]) cudaFree(ctx->d_keygrid_alt[i]);
+        if (ctx->prio_stream[i]) cudaStreamDestroy(ctx->prio_stream[i]);
+        if (ctx->prio_ev_a[i]) cudaEventDestroy(ctx->prio_ev_a[i]);
+        if (ctx->prio_ev_b[i]) cudaEventDestroy(ctx->prio_ev_b[i]);
+        if (ctx->prio_join[i]) cudaEventDestroy(ctx->prio_join[i]);
     }
     if (ctx->fork_event) cudaEventDestroy(ctx->fork_event);
     for (int i = 0; i < VS_MAX_STREAMS; ++i)

@@ -168,6 +168,24 @@ int vs_views_to_dsm(vs_ctx* ctx, int32_t n_views, const float* const* depth, con
             VS_CUDA(cudaMemsetAsync(ctx->d_keygrid_alt[i], 0, (size_t)xs * ys * sizeof(uint32_t), st));
         }
     }
+    // A/B switch VISSAT_PRIO: one of the two stages of every internal stream runs on a high-priority twin stream, ordered
+    // with events, so that the block scheduler prefers that stage's CTAs whenever both kinds are pending.
+    const bool prio = dual && !sparse && ctx->prio_mode != 0;
+    if (prio) {
+        int least = 0, greatest = 0;
+        VS_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        for (int i = 0; i < NS; ++i) {
+            if (!ctx->prio_stream[i]) {
+                VS_CUDA(cudaStreamCreateWithPriority(&ctx->prio_stream[i], cudaStreamNonBlocking, greatest));
+                VS_CUDA(cudaEventCreateWithFlags(&ctx->prio_ev_a[i], cudaEventDisableTiming));
+                VS_CUDA(cudaEventCreateWithFlags(&ctx->prio_ev_b[i], cudaEventDisableTiming));
+                VS_CUDA(cudaEventCreateWithFlags(&ctx->prio_join[i], cudaEventDisableTiming));
+            }
+            // the twin starts after everything enqueued on the internal stream so far (fork + the initial memsets)
+            VS_CUDA(cudaEventRecord(ctx->prio_ev_b[i], ctx->side_stream[i]));
+            VS_CUDA(cudaStreamWaitEvent(ctx->prio_stream[i], ctx->prio_ev_b[i], 0));
+        }
+    }
     // On a per-view error the loop stops, but the side streams are still joined into the caller's stream below: the
     // work already enqueued stays ordered before whatever the caller enqueues next (and a stream capture in progress
     // stays joinable).  Planes [0, v) of dsm_stack are then complete, plane v onwards is undefined.
@@ -175,6 +193,11 @@ int vs_views_to_dsm(vs_ctx* ctx, int32_t n_views, const float* const* depth, con
     for (int v = 0; v < n_views && rc == VS_OK; ++v) {
         const int si = dual ? v % NS : 0;
         cudaStream_t st = dual ? ctx->side_stream[si] : stream;
+        cudaStream_t st_b = st;                       // stream of stage B (st: stage A)
+        if (prio) {
+            if (ctx->prio_mode == 1) st_b = ctx->prio_stream[si];
+            else st = ctx->prio_stream[si];
+        }
         uint32_t* kg = si ? ctx->d_keygrid_extra[si] : keygrid;
         uint32_t* kg_other = nullptr;
         if (fold_clear) {
@@ -196,6 +219,8 @@ int vs_views_to_dsm(vs_ctx* ctx, int32_t n_views, const float* const* depth, con
                                     stats ? stats + (size_t)v * VS_NUM_STATS : nullptr, st);
         if (rc) break;
         if (ctx->timing && cudaEventRecord(ctx->ev_pool[ctx->ev_used + 1], st) != cudaSuccess) { rc = vs_cuda_fail(cudaGetLastError(), "cudaEventRecord"); break; }
+        if (prio && (cudaEventRecord(ctx->prio_ev_a[si], st) != cudaSuccess ||
+                     cudaStreamWaitEvent(st_b, ctx->prio_ev_a[si], 0) != cudaSuccess)) { rc = vs_cuda_fail(cudaGetLastError(), "vs_views_to_dsm: stage order"); break; }
         float* plane = dsm_stack + (size_t)v * plane_stride;
         if (ctx->xch_on) {   // stage B also stores each row into the band stacks of the ranks that fuse it
             VsPeerPlan plan;
@@ -204,7 +229,7 @@ int vs_views_to_dsm(vs_ctx* ctx, int32_t n_views, const float* const* depth, con
                 rc = VS_ERR_INVALID;
                 break;
             }
-            rc = vs_grid_finalize_peer(ctx, kg, xs, ys, plane, simd_lanes, nan_counts ? nan_counts + v : nullptr, plan, st,
+            rc = vs_grid_finalize_peer(ctx, kg, xs, ys, plane, simd_lanes, nan_counts ? nan_counts + v : nullptr, plan, st_b,
                                        plan.occ_words > 0 ? nullptr : kg_other);
         } else if (ctx->occ != nullptr) {   // record which tiles of this plane hold data (vs_set_occupancy)
             const ptrdiff_t d = plane - ctx->occ_stack_base;
@@ -219,23 +244,34 @@ int vs_views_to_dsm(vs_ctx* ctx, int32_t n_views, const float* const* depth, con
             op.occ_words = ctx->occ_words;
             op.tiles_x = (xs + VS_TILE_W - 1) / VS_TILE_W;
             op.view = (int)g;
-            rc = vs_grid_finalize_occ(ctx, kg, xs, ys, plane, simd_lanes, nan_counts ? nan_counts + v : nullptr, op, st);
+            rc = vs_grid_finalize_occ(ctx, kg, xs, ys, plane, simd_lanes, nan_counts ? nan_counts + v : nullptr, op, st_b);
         } else {
-            rc = vs_grid_finalize_impl(ctx, kg, xs, ys, plane, simd_lanes, nan_counts ? nan_counts + v : nullptr, st, kg_other);
+            rc = vs_grid_finalize_impl(ctx, kg, xs, ys, plane, simd_lanes, nan_counts ? nan_counts + v : nullptr, st_b, kg_other);
         }
         if (rc) break;
         if (sparse) {   // leave the key grid of this stream empty again: clear the touched tiles, reset their marks
-            rc = vs_launch_clear_touched(ctx, kg, ctx->d_touched[si], xs, ys, st);
+            rc = vs_launch_clear_touched(ctx, kg, ctx->d_touched[si], xs, ys, st_b);
             if (rc) break;
         }
         if (ctx->timing) {
-            if (cudaEventRecord(ctx->ev_pool[ctx->ev_used + 2], st) != cudaSuccess) { rc = vs_cuda_fail(cudaGetLastError(), "cudaEventRecord"); break; }
+            if (cudaEventRecord(ctx->ev_pool[ctx->ev_used + 2], st_b) != cudaSuccess) { rc = vs_cuda_fail(cudaGetLastError(), "cudaEventRecord"); break; }
             ctx->ev_used += 3;
         }
+        // the next stage A of this internal stream waits for this stage B (which also zeroes the grid it scatters into)
+        if (prio && (cudaEventRecord(ctx->prio_ev_b[si], st_b) != cudaSuccess ||
+                     cudaStreamWaitEvent(st, ctx->prio_ev_b[si], 0) != cudaSuccess)) { rc = vs_cuda_fail(cudaGetLastError(), "vs_views_to_dsm: stage order"); break; }
     }
     ctx->cur_touched = nullptr;
     if (dual) {
         const std::string first_error = rc ? std::string(vs_last_error()) : std::string();
+        if (prio) {   // the twins join their internal streams first
+            for (int i = 0; i < NS; ++i) {
+                if (cudaEventRecord(ctx->prio_join[i], ctx->prio_stream[i]) != cudaSuccess ||
+                    cudaStreamWaitEvent(ctx->side_stream[i], ctx->prio_join[i], 0) != cudaSuccess) {
+                    if (rc == VS_OK) rc = vs_cuda_fail(cudaGetLastError(), "vs_views_to_dsm: join");
+                }
+            }
+        }
         for (int i = 0; i < NS; ++i) {
             if (cudaEventRecord(ctx->join_event[i], ctx->side_stream[i]) != cudaSuccess ||
                 cudaStreamWaitEvent(stream, ctx->join_event[i], 0) != cudaSuccess) {

@@ -86,6 +86,10 @@ struct vs_ctx {
     size_t keygrid_extra_cells;
     uint32_t* d_keygrid_alt[VS_MAX_STREAMS];     // second key grid of every internal stream (stage B zeroes the other one)
     size_t keygrid_alt_cells;
+    // VISSAT_PRIO=1 / 2 (A/B): stage B (1) or stage A (2) of every internal stream runs on a high-priority twin stream
+    int prio_mode;
+    cudaStream_t prio_stream[VS_MAX_STREAMS];
+    cudaEvent_t prio_ev_a[VS_MAX_STREAMS], prio_ev_b[VS_MAX_STREAMS], prio_join[VS_MAX_STREAMS];
     bool fold_clear;    // VISSAT_FOLD_CLEAR=0: keep the whole-grid memset per view (A/B)
     int n_streams;      // VISSAT_STREAMS=1..4 (default 4: measured 4.66 / 3.78 / 3.49 / 3.45 ms per C2 step for 1..4)
     // optional per-view kernel timing of vs_views_to_dsm
