@@ -136,3 +136,27 @@ def test_read_model_text(tmp_path):
     assert p.xyz.shape == (3,) and p.image_ids.size == p.point2D_idxs.size >= 2
     with pytest.raises(NotImplementedError):
         read_model(base, ext='.bin')
+
+
+def test_utm_to_latlon_known_values_of_the_utm_package():
+    """`utm.to_latlon` (utm==0.4.2, requirements.txt; called by stereo_pipeline.py:198-205) is absent from the image.  Its
+    own test-suite (test/test_utm.py: KnownValues, compared to 4 decimals there) anchors the restatement in
+    stereo_pipeline.utm_to_latlon: eastings / northings rounded to a metre <-> latitude / longitude to 5 decimals.  The same
+    vectors are also run through the oracle's exact inverse (pinned to the 50-digit map), which must agree with the
+    restated series to < 5e-8 deg away from the pole-ward limit of UTM."""
+    from oracle import geodesy
+    from vissatsatellitestereo_b200.stereo_pipeline import utm_to_latlon
+    known = [((50.77535, 6.08389), (294409, 5628898, 32, True)),        # Aachen
+             ((40.71435, -74.00597), (583960, 4507523, 18, True)),      # New York
+             ((-41.28646, 174.77624), (313784, 5427057, 60, False)),    # Wellington
+             ((-33.92487, 18.42406), (261878, 6243186, 34, False)),     # Capetown
+             ((-32.89018, -68.84405), (514586, 6360877, 19, False)),    # Mendoza
+             ((64.83778, -147.71639), (466013, 7190568, 6, True)),      # Fairbanks
+             ((56.79680, -5.00601), (377486, 6296562, 30, True)),       # Ben Nevis
+             ((84.0, -5.00601), (476594, 9328501, 30, True))]           # latitude 84
+    for (lat, lon), (e, n, zone, northern) in known:
+        got = utm_to_latlon(e, n, zone, northern)
+        assert abs(got[0] - lat) < 5e-5 and abs(got[1] - lon) < 5e-5, (lat, lon, got)
+        exact = geodesy.utm_inverse(e, n, zone, not northern)
+        tol = 5e-8 if abs(lat) < 80 else 5e-7
+        assert abs(got[0] - float(exact[0])) < tol and abs(got[1] - float(exact[1])) < tol, (lat, lon, got, exact)

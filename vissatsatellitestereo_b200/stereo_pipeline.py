@@ -5,8 +5,9 @@ asking for it is an error.
 
 `write_aoi` goes through `utm.to_latlon` (utm==0.4.2) in the reference; that package is not in /root/reference, so
 its series is restated below from the published algorithm it implements (Snyder, USGS PP-1395, eqs. 8-17…8-25 and
-3-24/7-19: footpoint latitude + truncated series in D) -- parity unpinned: no reference-run vector exists for it; the
-test anchors it on the PROJ inverse (agreement < 5e-8 deg).  It only fixes the ENU origin stored in aoi.json.
+3-24/7-19: footpoint latitude + truncated series in D).  No reference-run vector exists for it; the tests anchor it on the
+package's own known-value vectors (metre-rounded) and on the exact inverse of the data path (agreement < 5e-8 deg).  It
+only fixes the ENU origin stored in aoi.json.
 """
 import json
 import logging
