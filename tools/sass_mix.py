@@ -11,12 +11,15 @@ import subprocess
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BUILD = os.path.join(REPO, 'vissatsatellitestereo_b200', 'csrc', 'build')
-KERNELS = [('rasterize.o', 'k_unproject_scatterILi3ELi1', 'K1 k_unproject_scatter<3,1>'),
+KERNELS = [('rasterize.o', 'k_unproject_scatterILi3ELi1ELb1', 'K1 k_unproject_scatter<3,1,lean>'),
+           ('rasterize.o', 'k_unproject_scatterILi3ELi1ELb0', 'K1 k_unproject_scatter<3,1,full> (audited / sparse mode)'),
            ('finalize.o', 'k_grid_finalizeIjN5vsfin6NoSink', 'K2 k_grid_finalize<u32>'),
            ('finalize.o', 'k_grid_finalizeIjN5vsfin8PeerSink', 'K2 k_grid_finalize<u32, PeerSink>'),
            ('finalize.o', 'k_median3x3', 'K4 k_median3x3'),
            ('fuse.o', 'k_fuse_mediumILi52', 'K3 k_fuse_medium<52>'),
-           ('fuse.o', 'k_fuse_largeILi4ELi52', 'K3 k_fuse_large<4,52>')]
+           ('fuse.o', 'k_fuse_pairILi104', 'K3 k_fuse_pair<104>'),
+           ('fuse.o', 'k_fuse_largeILi8ELi52', 'K3 k_fuse_large<8,52>'),
+           ('stage_ab.o', 'k_stage_abILi3ELi1EN5vsfin6NoSink', 'K1||K2 k_stage_ab<3,1> (opt-in)')]
 PIPE = {'fma': ('FFMA', 'FFMA2', 'FMUL', 'FMUL2', 'FADD', 'FADD2', 'IMAD', 'HFMA2'),
         'alu': ('IADD3', 'VIADD', 'LOP3', 'SHF', 'PRMT', 'FMNMX', 'FMNMX3', 'VIMNMX', 'VIMNMX3', 'ISETP', 'FSETP', 'SEL', 'FSEL',
                 'PLOP3', 'LEA', 'POPC', 'FLO', 'BREV', 'IABS', 'MOV', 'DSETP'),
