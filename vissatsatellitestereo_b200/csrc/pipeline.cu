@@ -148,8 +148,10 @@ int vs_views_to_dsm(vs_ctx* ctx, int32_t n_views, const float* const* depth, con
     // Dense mode: every internal stream alternates between TWO key grids.  Stage B of a view zeroes, tile by tile, the grid
     // the previous view of its stream used (k_grid_finalize: clear_other), which the next view's stage A then scatters
     // into -- instead of a whole-grid memset in front of every stage A (50 x 16.8 MB memset nodes per C2 step).  Both
-    // grids of a stream are zeroed once per call.  (Key-space / TMA variants of stage B keep the memset per view.)
-    const bool fold_clear = !sparse && ctx->k2_mode != 2 && ctx->no_tma && ctx->fold_clear;
+    // grids of a stream are zeroed once per call.  (The key-space / TMA variants of stage B and the occupancy-marking launch
+    // of the float-space kernel have no clear_other: those calls keep the memset per view.)
+    const bool fold_clear = !sparse && ctx->occ == nullptr && !(ctx->xch_on && ctx->xch.occ_words > 0) && ctx->k2_mode != 2 &&
+                            ctx->no_tma && ctx->fold_clear;
     if (fold_clear) {
         const int n_used = dual ? NS : 1;
         if (ctx->keygrid_alt_cells < (size_t)xs * ys) {
